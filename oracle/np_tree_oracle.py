@@ -1,0 +1,361 @@
+"""numpy restatement of the reference hot path -- TEST INFRASTRUCTURE ONLY.
+
+Not a product path: see ``oracle/__init__.py`` for who may import this.
+
+All "ref:" citations are paths below /root/reference/ (yupbank/np_decision_tree).
+The arithmetic (operation order, dtypes, tie rules) follows the reference
+exactly; the code organisation is our own.  Parity pinning: replayed against
+fixtures produced by the reference itself (tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import heapq
+import os
+import subprocess
+from collections import namedtuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# ref: decision_tree/one.py:5-6 -- the five parallel arrays of the tree.
+TreeFields = namedtuple(
+    "TreeFields", "children_left children_right feature threshold value")
+
+
+class TreeArrays:
+    """Tree container with the reference's layout (ref: decision_tree/one.py:9-24).
+
+    ``tree_`` holds five arrays of length ``2**(max_depth+1) - 1``; unused
+    slots keep -1 / -1 / -2 / -2.0; ``value`` is only defined on leaves.
+    ``max_node_`` is the id of the last node created (node_count - 1).
+    """
+
+    def __init__(self, max_depth):
+        slots = 2 ** (max_depth + 1) - 1
+        self.tree_ = TreeFields(
+            np.full(slots, -1, dtype=np.int64),
+            np.full(slots, -1, dtype=np.int64),
+            np.full(slots, -2, dtype=np.int64),
+            np.full(slots, -2.0, dtype=np.float64),
+            # the reference leaves this uninitialised (np.empty); NaN makes
+            # accidental use of a non-leaf value visible in tests
+            np.full(slots, np.nan, dtype=np.float64),
+        )
+        self.max_node_ = -1
+
+    @property
+    def node_count(self):
+        return self.max_node_ + 1
+
+    def leaf_mask(self):
+        m = np.zeros(self.tree_.feature.shape[0], dtype=bool)
+        m[: self.node_count] = self.tree_.children_left[: self.node_count] == -1
+        return m
+
+
+# --------------------------------------------------------------------------
+# sort
+# --------------------------------------------------------------------------
+def argsort_columns(X, kind=None):
+    """Per-column sort permutation (ref: decision_tree/one.py:139).
+
+    The reference uses numpy's default (unstable) kind, so the order among
+    equal feature values is unspecified there.  ``kind='stable'`` is what the
+    CUDA radix sort produces; both agree on columns with distinct values.
+    """
+    return np.argsort(X, axis=0, kind=kind)
+
+
+# --------------------------------------------------------------------------
+# L2 (MSE) split search
+# --------------------------------------------------------------------------
+def l2_weights(n):
+    """1 / (left_count * right_count) for split positions 0..n-2.
+
+    ref: decision_tree/one.py:52-53 (np_gene).  left_count is float32,
+    right_count int64; the product promotes to float64.
+    """
+    left_count = np.arange(1, n, dtype=np.float32)
+    right_count = np.arange(n - 1, 0, -1)
+    return np.reciprocal(left_count * right_count)
+
+
+def l2_best_split(prefix):
+    """Best (position, feature, gain) from column prefix sums.
+
+    ref: decision_tree/one.py:56-63 (best_variance_improvements).
+    ``prefix[k, f]`` = sum of y over the first k+1 rows of feature f's order.
+    The node total is read from the LAST column (one.py:57).  Ties: lowest
+    feature inside a position (one.py:59), then lowest position (one.py:62).
+    """
+    n = prefix.shape[0]
+    node_mean = prefix[-1][-1] / n
+    expected = np.arange(1, n + 1) * node_mean
+    dev = np.abs(prefix - expected[:, np.newaxis])
+    feat_of_pos = np.argmax(dev, axis=1)
+    dev_of_pos = dev[np.arange(n), feat_of_pos]
+    gain = l2_weights(n) * np.square(dev_of_pos)[:-1]
+    k = np.argmax(gain)
+    return k, feat_of_pos[k], gain[k]
+
+
+def l2_best_split_ratio(prefix):
+    """The ``v != 1`` search with float32 sqrt ratios.
+
+    ref: decision_tree/one.py:81-93 (best_variance_improvements_v2).  Flat
+    row-major argmax => lowest position, then lowest feature.
+    """
+    n = prefix.shape[0]
+    node_mean = prefix[-1][-1] / n
+    lc = np.arange(1, n, dtype=np.float32)
+    rc = np.arange(n - 1, 0, -1, dtype=np.float32)
+    scale_sum = np.sqrt(np.reciprocal(lc * rc))[:, np.newaxis]
+    scale_mean = np.sqrt(lc / rc)[:, np.newaxis]
+    score = np.abs(scale_sum * prefix[:-1] - node_mean * scale_mean)
+    k, f = np.unravel_index(np.argmax(score), score.shape)
+    return k, f, np.square(score[k, f])
+
+
+def l2_split_node(orders, X, y, v=1):
+    """ref: decision_tree/one.py:96-107 (greedy_regression_split)."""
+    prefix = np.cumsum(y[orders], axis=0)
+    search = l2_best_split if v == 1 else l2_best_split_ratio
+    k, f, gain = search(prefix)
+    threshold = X[orders[k, f], f]
+    left_rows = orders[:, f][: k + 1]
+    return threshold, f, gain, left_rows
+
+
+# --------------------------------------------------------------------------
+# node partition
+# --------------------------------------------------------------------------
+def partition_orders(orders, left_rows, n_samples):
+    """Stable split of every column of ``orders`` into (left, right).
+
+    ref: decision_tree/one.py:110-118 (split_orders).
+    """
+    goes_left = np.zeros(n_samples, dtype=bool)
+    goes_left[left_rows] = True
+    mask = goes_left[orders]
+    n_left = left_rows.shape[0]
+    n_right = orders.shape[0] - n_left
+    left = orders.T[mask.T].reshape(-1, n_left).T
+    right = orders.T[~mask.T].reshape(-1, n_right).T
+    return left, right
+
+
+# --------------------------------------------------------------------------
+# tree growth (shared driver; ref: one.py:135-162, strategy_l1.py:143-200)
+# --------------------------------------------------------------------------
+def _grow(X, y, orders, max_depth, min_improvement, min_sample_leaf,
+          split_fn, leaf_fn):
+    tree = TreeArrays(max_depth)
+    t = tree.tree_
+    # LIFO work list of (orders, parent, is_left, depth): pre-order, left first
+    # (ref: one.py:141-160; node ids from one.py:26-31)
+    pending = [(orders, None, True, 0)]
+    while pending:
+        node_orders, parent, is_left, depth = pending.pop()
+        tree.max_node_ += 1
+        node = tree.max_node_
+        if parent is not None:
+            (t.children_left if is_left else t.children_right)[parent] = node
+        # leaf test: rows <= min_sample_leaf or depth limit (one.py:40-46,145)
+        if node_orders.shape[0] <= min_sample_leaf or depth >= max_depth:
+            t.value[node] = leaf_fn(y[node_orders])
+            continue
+        threshold, f, score, left_rows = split_fn(node_orders, X, y)
+        # one.py:150 / strategy_l1.py:158 -- same "<" test for both criteria
+        if score < min_improvement:
+            t.value[node] = leaf_fn(y[node_orders])
+            continue
+        t.threshold[node] = threshold
+        t.feature[node] = f
+        left, right = partition_orders(node_orders, left_rows, y.shape[0])
+        pending.append((right, node, False, depth + 1))
+        pending.append((left, node, True, depth + 1))
+    return tree
+
+
+def fit_l2(X, y, max_depth=2, max_feature=100, min_improvement=1e-7,
+           min_sample_leaf=1, v=1, sort_kind=None):
+    """ref: decision_tree/one.py:135-162 (build_regression_tree).
+
+    ``max_feature`` is accepted and ignored, as in the reference.
+    Leaf value: np.mean over the (n, F) gather (one.py:132,146).
+    """
+    orders = argsort_columns(X, kind=sort_kind)
+    return _grow(X, y, orders, max_depth, min_improvement, min_sample_leaf,
+                 lambda o, X_, y_: l2_split_node(o, X_, y_, v), np.mean)
+
+
+# --------------------------------------------------------------------------
+# running median (native in the reference)
+# --------------------------------------------------------------------------
+def running_median_pairs_py(seq):
+    """Pure-Python (lower, upper) running median; small inputs only.
+
+    ref: decision_tree/np_stream_median.pyx:8-39 (cummedian) and
+    decision_tree/stream_median.py:33-64,90-92.  Two heaps: ``low`` is a
+    max-heap (stored negated), ``high`` a min-heap.
+    """
+    n = len(seq)
+    out = np.zeros((n, 2), dtype=np.float64)
+    low, high = [], []
+    for i in range(n):
+        x = float(seq[i])
+        if not low or x <= -low[0]:
+            heapq.heappush(low, -x)
+        else:
+            heapq.heappush(high, x)
+        if len(low) > len(high) + 1:
+            heapq.heappush(high, -heapq.heappop(low))
+        elif len(high) > len(low) + 1:
+            heapq.heappush(low, -heapq.heappop(high))
+        if len(low) == len(high):
+            out[i, 0], out[i, 1] = -low[0], high[0]
+        elif len(low) > len(high):
+            out[i, 0] = out[i, 1] = -low[0]
+        else:
+            out[i, 0] = out[i, 1] = high[0]
+    return out
+
+
+_C_LIB = None
+
+
+def build_c_oracle(force=False):
+    """Compile oracle/running_median.c -> oracle/_build/liboracle_cpu.so."""
+    out_dir = os.path.join(_HERE, "_build")
+    so = os.path.join(out_dir, "liboracle_cpu.so")
+    src = os.path.join(_HERE, "running_median.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-std=c11", "-shared", "-fPIC", "-o", so, src])
+    return so
+
+
+def _c_lib():
+    global _C_LIB
+    if _C_LIB is None:
+        lib = ctypes.CDLL(build_c_oracle())
+        lib.oracle_running_median_pairs.restype = ctypes.c_int
+        lib.oracle_running_median_pairs.argtypes = [
+            ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
+        _C_LIB = lib
+    return _C_LIB
+
+
+def running_median_pairs(seq):
+    """(n, 2) array of (lower, upper) running medians (C restatement).
+
+    ref: decision_tree/np_stream_median.pyx:8-39.  Prefix of length m:
+    lower = order statistic floor((m-1)/2), upper = floor(m/2).
+    """
+    a = np.ascontiguousarray(seq, dtype=np.float64)
+    n = a.shape[0]
+    out = np.zeros((n, 2), dtype=np.float64)
+    if n:
+        rc = _c_lib().oracle_running_median_pairs(
+            a.ctypes.data, n, 1, out.ctypes.data)
+        if rc != 0:
+            raise MemoryError("oracle_running_median_pairs failed")
+    return out
+
+
+def _median_pairs_columns(ys):
+    """(n, F) -> two (n, F) arrays: lower / upper running median per column.
+
+    ref: strategy_l1.py:88 (np.apply_along_axis(cummedian, 0, ys)).
+    """
+    n, F = ys.shape
+    lo = np.empty((n, F), dtype=np.float64)
+    hi = np.empty((n, F), dtype=np.float64)
+    for f in range(F):
+        pairs = running_median_pairs(ys[:, f])
+        lo[:, f] = pairs[:, 0]
+        hi[:, f] = pairs[:, 1]
+    return lo, hi
+
+
+# --------------------------------------------------------------------------
+# L1 (MAE) split search
+# --------------------------------------------------------------------------
+def l1_best_split(ys):
+    """Best (position, feature, children L1 cost) -- cost is MINIMISED.
+
+    ref: decision_tree/strategy_l1.py:87-122 (best_l1_improvements_v2); the
+    pure-Python twin strategy_l1.py:49-84 yields identical results.
+    """
+    n, F = ys.shape
+    # prefix side: cost(prefix + y) = cost(prefix) + dist(y, [lo, hi]) with
+    # the pair of the prefix BEFORE y joins (strategy_l1.py:89-100)
+    lo_p, hi_p = _median_pairs_columns(ys)
+    nxt = ys[1:]
+    lo_b, hi_b = lo_p[:-1], hi_p[:-1]
+    left_cost = np.cumsum(
+        np.where(nxt <= lo_b, lo_b - nxt, 0) + np.where(nxt >= hi_b, nxt - hi_b, 0),
+        axis=0)
+    left_cost = np.concatenate([np.zeros((1, F)), left_cost])
+    # suffix side: the pair already CONTAINS y (strategy_l1.py:103-117)
+    lo_s, hi_s = _median_pairs_columns(ys[::-1])
+    lo_s, hi_s = lo_s[::-1], hi_s[::-1]
+    right_cost = np.cumsum(
+        (np.where(ys <= lo_s, hi_s - ys, 0) + np.where(ys >= hi_s, ys - lo_s, 0))[::-1],
+        axis=0)[::-1]
+    # strategy_l1.py:119-121: total cost of the two children, flat argmin
+    cost = right_cost[1:] + left_cost[:-1]
+    k, f = np.unravel_index(np.argmin(cost), cost.shape)
+    return k, f, cost[k, f]
+
+
+def l1_split_node(orders, X, y):
+    """ref: decision_tree/strategy_l1.py:134-140 (greedy_regression_split_v2)."""
+    k, f, cost = l1_best_split(y[orders])
+    threshold = X[orders[k, f], f]
+    left_rows = orders[: k + 1, f]
+    return threshold, f, cost, left_rows
+
+
+def fit_l1(X, y, max_depth=2, max_feature=100, min_improvement=1e-7,
+           min_sample_leaf=1, leaf_from_data=np.median, sort_kind=None):
+    """ref: decision_tree/strategy_l1.py:173-200 (build_regression_tree_v2);
+    strategy_l1.py:143-170 (build_regression_tree) builds the same tree."""
+    orders = argsort_columns(X, kind=sort_kind)
+    return _grow(X, y, orders, max_depth, min_improvement, min_sample_leaf,
+                 l1_split_node, leaf_from_data)
+
+
+# --------------------------------------------------------------------------
+# inference
+# --------------------------------------------------------------------------
+def _descend(data, tree):
+    """Level-synchronous traversal; returns the final node per row.
+
+    ref: decision_tree/utils.py:15-30 / 34-47.  Left iff x <= threshold;
+    a row stops where the chosen child is -1.  Shape quirk kept: if nothing
+    ever moves (root-only tree) the result has shape (1,).
+    """
+    t = tree.tree_
+    rows = np.arange(data.shape[0], dtype=np.int32)
+    at = np.zeros(1, dtype=np.int32)
+    while True:
+        go_left = data[rows, t.feature[at]] <= t.threshold[at]
+        nxt = np.where(go_left, t.children_left[at], t.children_right[at])
+        moves = nxt != -1
+        if not np.any(moves):
+            return at
+        at = np.where(moves, nxt, at)
+
+
+def predict(data, tree):
+    """ref: decision_tree/utils.py:15-31 (inference)."""
+    return tree.tree_.value[_descend(data, tree)].ravel()
+
+
+def predict_leaf(data, tree):
+    """ref: decision_tree/utils.py:34-48 (inference_leaf)."""
+    return _descend(data, tree)
