@@ -1,0 +1,176 @@
+/* b200dt.h -- C ABI of libb200tree.so: the B200 (sm_100a) regression-tree hot path.
+ *
+ * This is the drop-in boundary for the ONE hot path of yupbank/np_decision_tree:
+ * exhaustive L2 / L1 split search, node partition and batched inference.  The
+ * reference has no FFI of its own (plain Python functions + one Cython module),
+ * so each entry point cites the reference function(s) it replaces, as
+ * path:line below /root/reference/.  The Python mirror of the reference API that
+ * binds these symbols with ctypes is np_decision_tree_b200/decision_tree/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     b200dt_last_error(ctx) (ctx may be NULL for errors of b200dt_create).
+ *   - `space` arguments: B200DT_HOST pointers are plain host memory (numpy),
+ *     B200DT_DEVICE pointers are device memory on the context's GPU (e.g. a
+ *     torch CUDA tensor's data_ptr()).  Caller buffers are never freed or written
+ *     unless documented as outputs.
+ *   - there is NO CPU fallback: without a usable CUDA device b200dt_create fails.
+ *   - a context is not re-entrant; one context = one host thread, one GPU, one stream.
+ *   - row ids are int32 on the device (N < 2^31, like ref utils.py:19 / pyx:9).
+ */
+#ifndef B200DT_H
+#define B200DT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DT_ABI_VERSION 1
+
+#define B200DT_HOST 0
+#define B200DT_DEVICE 1
+
+#define B200DT_L2 0 /* MSE: ref decision_tree/one.py                  */
+#define B200DT_L1 1 /* MAE: ref decision_tree/strategy_l1.py          */
+
+typedef struct b200dt_ctx b200dt_ctx;
+
+/* ---- context ---------------------------------------------------------------- */
+int b200dt_abi_version(void);
+int b200dt_create(b200dt_ctx **out, int device_id);
+void b200dt_destroy(b200dt_ctx *ctx);
+const char *b200dt_last_error(const b200dt_ctx *ctx);
+/* Launch on this cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int b200dt_set_stream(b200dt_ctx *ctx, void *cuda_stream);
+int b200dt_synchronize(b200dt_ctx *ctx);
+
+/* ---- K1: per-column argsort --------------------------------------------------
+ * replaces: np.argsort(X, axis=0)     ref one.py:139, strategy_l1.py:147,177
+ * X is (N, F) float64, row stride ldx elements.  Stable LSD radix sort on the
+ * order-preserving uint64 image of the key (== np.argsort(kind='stable'); equal to
+ * the reference's default kind whenever a column has distinct values).
+ * orders_out: (N, F) int64 row-major, like the reference's `orders`. */
+int b200dt_argsort_columns(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64_t ldx,
+                           int x_space, int64_t *orders_out, int out_space);
+
+/* ---- K2: L2 split search of ONE node -----------------------------------------
+ * replaces: greedy_regression_split(orders, x, y, v)            ref one.py:96-107
+ *           best_variance_improvements / _v2 + np_gene          ref one.py:52-63,81-93
+ * orders: (n, F) int64 row-major host array of row ids into X / y (N rows).
+ * variant: 1 = `v == 1`, anything else = the float32-ratio search (`v != 1`).
+ * outputs: best sorted position k (left child = first k+1 rows of column f),
+ * feature f, gain, threshold = X[orders[k,f], f].  Tie rule: max gain, then
+ * lowest k, then lowest f (one.py:59,62). */
+int b200dt_l2_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F,
+                         const double *X, int64_t ldx, const double *y, int64_t N, int variant,
+                         int64_t *out_k, int64_t *out_f, double *out_gain, double *out_threshold);
+
+/* ---- K3: L1 split search of ONE node, and the running median ------------------
+ * replaces: greedy_regression_split[_v2](orders, X, y)   ref strategy_l1.py:125-140
+ *           best_l1_improvements[_v2]                     ref strategy_l1.py:49-122
+ * out_cost = total L1 cost of the two children (minimised; ties lowest k, then f). */
+int b200dt_l1_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F,
+                         const double *X, int64_t ldx, const double *y, int64_t N,
+                         int64_t *out_k, int64_t *out_f, double *out_cost, double *out_threshold);
+/* replaces: np_stream_median.cummedian(arr)               ref np_stream_median.pyx:8-39
+ *           StreamMedian.__call__                          ref stream_median.py:90-92
+ * out: (n, 2) float64 (lower, upper) median of a[0..i]. */
+int b200dt_cummedian(b200dt_ctx *ctx, const double *a, int64_t n, int a_space, double *out,
+                     int out_space);
+
+/* ---- K4: stable node partition -------------------------------------------------
+ * replaces: split_orders(orders, index, n_samples)        ref one.py:110-118
+ * orders (n, F) int64 host; left_rows (n_left,) int64 host; outputs (n_left, F) and
+ * (n - n_left, F) int64 row-major host arrays. */
+int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F,
+                        const int64_t *left_rows, int64_t n_left, int64_t n_samples,
+                        int64_t *left_out, int64_t *right_out);
+
+/* ---- whole fit on one GPU --------------------------------------------------------
+ * replaces: one.build_regression_tree / build_regression_tree_v1_5   ref one.py:135-192
+ *           strategy_l1.build_regression_tree / _v2                  ref strategy_l1.py:143-200
+ * Tree arrays are caller-allocated host arrays of length `capacity`
+ * (= 2**(max_depth+1) - 1), pre-filled by the caller with the reference's sentinels
+ * (-1, -1, -2, -2.0; ref one.py:17-20).  Node ids are pre-order, left first
+ * (one.py:26-31,157-160).  `value` is written for every node (the reference only
+ * defines it on leaves).  *node_count = max_node_ + 1. */
+int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F,
+               int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
+               int64_t min_sample_leaf, int variant, int64_t *children_left,
+               int64_t *children_right, int64_t *feature, double *threshold, double *value,
+               int64_t capacity, int64_t *node_count);
+
+/* ---- feature-sharded fit: one session per GPU, driven level by level --------------
+ * The host loop of ref one.py:141-160, level-synchronous.  Each rank owns columns
+ * [col_offset, col_offset + F_local) of a global (N, F_global) matrix; X points at the
+ * rank's slice.  Per level:
+ *   search  -> local best candidate per live node (device array the caller all-gathers)
+ *   decide  -> every rank feeds the gathered candidates; the library picks each node's
+ *              winner with the reference's tie rule and the owner marks the left rows in
+ *              the side mask (device, N/32 words, caller sum-all-reduces it)
+ *   partition -> stable partition of every local column by the reduced mask.
+ * last_col: the rank's own copy of global column F_global-1, (N,) float64 with stride
+ * last_col_ld (the reference reads the node total in that column's order, one.py:57);
+ * NULL when the rank owns that column. */
+typedef struct b200dt_candidate {
+    double gain;      /* L2: variance gain (maximised); L1: children cost (minimised) */
+    double aux;       /* L2: |S - (k+1)*mean| of the candidate (in-row tie rule)        */
+    double left_sum;  /* L2: sum of y over the left rows                               */
+    double gain2;     /* best score among the OTHER local candidates (near-tie check)  */
+    double threshold; /* X[orders[k,f], f]                                             */
+    int32_t k;        /* sorted position                                               */
+    int32_t f;        /* GLOBAL feature index                                          */
+    int32_t exact;    /* 1: scores follow the reference's sequential fp64 order         */
+    int32_t pad;
+} b200dt_candidate;
+
+int b200dt_session_begin(b200dt_ctx *ctx, const double *X, const double *y, int64_t N,
+                         int64_t F_local, int64_t ldx, int space, int criterion, int max_depth,
+                         double min_improvement, int64_t min_sample_leaf, int variant,
+                         int64_t col_offset, int64_t F_global, const double *last_col,
+                         int64_t last_col_ld);
+/* number of nodes awaiting a search at the current level (0 => the tree is complete) */
+int b200dt_session_live(b200dt_ctx *ctx, int64_t *n_live);
+/* d_out: device array of n_live candidates */
+int b200dt_session_search(b200dt_ctx *ctx, b200dt_candidate *d_out);
+/* d_gathered: device array [n_ranks][n_live]; d_side_mask: device, (N+31)/32 uint32, zeroed
+ * by the library before marking.  *need_partition = 0 when no child needs a search. */
+int b200dt_session_decide(b200dt_ctx *ctx, const b200dt_candidate *d_gathered, int n_ranks,
+                          uint32_t *d_side_mask, int *need_partition, int *need_exact);
+/* re-search, with the reference's sequential arithmetic, the nodes `decide` reported as
+ * near-ties (need_exact != 0); afterwards gather and call decide again */
+int b200dt_session_search_exact(b200dt_ctx *ctx, b200dt_candidate *d_out);
+int b200dt_session_partition(b200dt_ctx *ctx, const uint32_t *d_side_mask);
+int b200dt_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right,
+                          int64_t *feature, double *threshold, double *value, int64_t capacity,
+                          int64_t *node_count);
+
+/* ---- K5: batched inference -------------------------------------------------------
+ * replaces: utils.inference / utils.inference_leaf        ref utils.py:15-31,34-48
+ * Go left iff X[row, feature[node]] <= threshold[node]; stop where the chosen child is -1.
+ * out_value (N,) float64 and/or out_leaf (N,) int32 may be NULL.  Tree arrays are host. */
+int b200dt_predict(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64_t ldx,
+                   int x_space, const int64_t *feature, const double *threshold,
+                   const int64_t *children_left, const int64_t *children_right,
+                   const double *value, int64_t n_nodes, double *out_value, int32_t *out_leaf,
+                   int out_space);
+
+/* ---- measurement -------------------------------------------------------------------
+ * When enabled, every kernel launch is bracketed by CUDA events on the launch stream;
+ * `get` synchronises and returns, per kernel class, the summed device time, the number of
+ * launches and the ALGORITHMIC bytes those launches moved. */
+int b200dt_profile_enable(b200dt_ctx *ctx, int on);
+int b200dt_profile_reset(b200dt_ctx *ctx);
+int b200dt_profile_count(void);
+const char *b200dt_profile_name(int kernel_class);
+int b200dt_profile_get(b200dt_ctx *ctx, int kernel_class, double *ms, int64_t *launches,
+                       double *alg_bytes);
+/* total kernel launches issued by the library on this context since the last reset */
+int64_t b200dt_launch_count(const b200dt_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DT_H */

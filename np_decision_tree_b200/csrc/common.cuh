@@ -1,0 +1,292 @@
+// Shared infrastructure of libb200tree: context, scratch buffers, per-kernel profiling,
+// warp helpers and the flag words of the single-pass (decoupled look-back) scans.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200dt.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---------------------------------------------------------------------------------------
+// kernel classes for the profiler (order = b200dt_profile_name ids)
+// ---------------------------------------------------------------------------------------
+enum KernelClass {
+    KC_SORT_PREPARE = 0,  // X (row-major f64) -> keys (feature-major u64) + digit histograms
+    KC_SORT_PASS,         // one 8-bit onesweep radix pass
+    KC_L2_SCAN,           // tiled segmented scan + gain + argmax (large nodes)
+    KC_L2_EXACT,          // sequential-order scan (small / near-tie nodes)
+    KC_FINALIZE,          // per-node arg-reduce of the partial candidates
+    KC_MARK,              // left-row side mask
+    KC_PARTITION,         // stable segmented partition
+    KC_PREDICT,           // batched traversal
+    KC_L1_RANK,           // node-local y ranks for the order-statistic descent
+    KC_L1_DESCENT,        // one bit level of the prefix/suffix median descent
+    KC_L1_COST,           // L1 cost scans + argmin
+    KC_MISC,              // small helpers (histogram scan, reductions, layout converts)
+    KC_COUNT
+};
+
+static const char *const kKernelClassNames[KC_COUNT] = {
+    "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
+    "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
+    "misc"};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ProfSlot {
+    cudaEvent_t a, b;
+    int kc;
+};
+
+struct Session;  // fit.cu
+
+struct b200dt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // profiling
+    bool prof_on = false;
+    std::vector<ProfSlot> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[KC_COUNT] = {0};
+    int64_t prof_launches[KC_COUNT] = {0};
+    double prof_bytes[KC_COUNT] = {0};
+    int64_t launches = 0;
+
+    // named grow-only scratch buffers (no allocation in steady state)
+    std::vector<DevBuf> scratch;
+    std::vector<void *> pinned;  // pinned host staging (index-matched with pinned_cap)
+    std::vector<size_t> pinned_cap;
+
+    Session *session = nullptr;
+
+    int fail(const char *what, cudaError_t e, const char *file, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+        err = buf;
+        return 1;
+    }
+    int fail_msg(const std::string &m) {
+        err = m;
+        return 1;
+    }
+};
+
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return ctx->fail(#call, e_, __FILE__, __LINE__); \
+    } while (0)
+
+#define CKR(call)               \
+    do {                        \
+        int r_ = (call);        \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+// scratch slot ids
+enum ScratchId {
+    SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
+    SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
+    SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_COUNT
+};
+
+static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {
+    if (ctx->scratch.size() < (size_t)SB_COUNT) ctx->scratch.resize(SB_COUNT);
+    DevBuf &b = ctx->scratch[id];
+    if (b.cap < bytes) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            CK(cudaMalloc(&b.p, want));
+        }
+        b.cap = want;
+        if (zero_new) CK(cudaMemsetAsync(b.p, 0, want, ctx->stream));
+    }
+    *out = b.p;
+    return 0;
+}
+
+static inline int scratch_free(b200dt_ctx *ctx, int id) {
+    if (ctx->scratch.size() <= (size_t)id) return 0;
+    DevBuf &b = ctx->scratch[id];
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    return 0;
+}
+
+// pinned host staging buffers, slot-indexed
+static inline int pinned_get(b200dt_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (ctx->pinned.size() <= (size_t)slot) {
+        ctx->pinned.resize(slot + 1, nullptr);
+        ctx->pinned_cap.resize(slot + 1, 0);
+    }
+    if (ctx->pinned_cap[slot] < bytes) {
+        if (ctx->pinned[slot]) CK(cudaFreeHost(ctx->pinned[slot]));
+        ctx->pinned[slot] = nullptr;
+        size_t want = bytes * 2 + 4096;
+        CK(cudaMallocHost(&ctx->pinned[slot], want));
+        ctx->pinned_cap[slot] = want;
+    }
+    *out = ctx->pinned[slot];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch bracket: counts launches; with profiling on, times them with events
+// ---------------------------------------------------------------------------------------
+struct LaunchScope {
+    b200dt_ctx *ctx;
+    int kc;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(b200dt_ctx *c, int kclass, double alg_bytes, int n_launches = 1) : ctx(c), kc(kclass) {
+        ctx->launches += n_launches;
+        if (!ctx->prof_on) return;
+        ctx->prof_launches[kc] += n_launches;
+        ctx->prof_bytes[kc] += alg_bytes;
+        auto take = [&]() {
+            cudaEvent_t e;
+            if (!ctx->prof_free.empty()) {
+                e = ctx->prof_free.back();
+                ctx->prof_free.pop_back();
+            } else {
+                cudaEventCreate(&e);
+            }
+            return e;
+        };
+        a = take();
+        b = take();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~LaunchScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof_pending.push_back({a, b, kc});
+    }
+};
+
+static inline void prof_drain(b200dt_ctx *ctx) {
+    for (auto &s : ctx->prof_pending) {
+        cudaEventSynchronize(s.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        ctx->prof_ms[s.kc] += ms;
+        ctx->prof_free.push_back(s.a);
+        ctx->prof_free.push_back(s.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL_MASK, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL_MASK, v, d); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
+
+// streaming loads / stores: the order arrays are read once per level
+__device__ __forceinline__ int ld_stream_i32(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// relaxed / acquire-release accesses for the look-back flag words
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// fast reciprocal, ~1e-15 relative: hardware seed + 2 Newton steps (approximate search only)
+__device__ __forceinline__ double rcp_fast(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------
+// node-level records shared by search / finalize / session
+// ---------------------------------------------------------------------------------------
+// Partial candidate written by a search block for one (tile or small node, column).
+struct Partial {
+    double score;   // L2 gain (maximise) or L1 cost (minimise)
+    double aux;     // L2: |S-(k+1)mean|; L1: unused
+    double lsum;    // L2: prefix sum at k
+    double score2;  // best score among the other candidates seen
+    int k;          // position inside the node, -1 = none
+    int f;          // local column
+};
+
+// cross-file entry points (host side)
+int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
+                        int *d_orders_out, int *d_orders_alt, int64_t col_stride);

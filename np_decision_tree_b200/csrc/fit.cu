@@ -1,0 +1,1019 @@
+// Host side of libb200tree: the level-synchronous tree-growing session, the one-GPU fit,
+// the single-node ops used by the parity tests, and the C ABI (include/b200dt.h).
+//
+// The reference grows the tree depth-first with one Python iteration per node
+// (ref decision_tree/one.py:141-160).  Here all nodes of a depth are contiguous segments of
+// one feature-major order array and are searched / partitioned by single launches; node ids
+// are renumbered to the reference's pre-order at the end (one.py:26-31,157-160).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "tree_kernels.cuh"
+
+int predict_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx, const int *d_feature,
+                   const int *d_left, const int *d_right, const double *d_threshold, const double *d_value,
+                   int n_nodes, double *d_out_value, int *d_out_leaf, double avg_path_hint);
+int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool exact_only);
+int l1_cummedian_device(b200dt_ctx *ctx, const double *d_a, int64_t n, double *d_out);
+int l1_leaf_medians(b200dt_ctx *ctx, Session *s);
+
+// nodes with at most this many rows are searched in the reference's sequential fp64 order
+static const int EXACT_MAX_ROWS = SC_TILE;
+// relative gap under which two candidate scores are treated as a tie to be re-searched exactly
+static const double NEAR_TIE_EPS = 1e-9;
+
+struct HNode {
+    int parent = -1;
+    int is_left = 1;
+    int depth = 0;
+    int start = 0;
+    int n = 0;
+    double total = 0.0;
+    int feature = -2;
+    double thr = -2.0;
+    int left = -1, right = -1;
+    double value = 0.0;
+    bool leaf = false;
+};
+
+struct Session {
+    int64_t N = 0;
+    int F_local = 0, F_store = 0, F_global = 0, col_offset = 0, total_col = 0, ycol = -1;
+    int criterion = B200DT_L2, max_depth = 0, variant = 1;
+    double min_improvement = 0.0;
+    int64_t min_sample_leaf = 1;
+    const double *dX = nullptr, *dy = nullptr;
+    int64_t ldx = 0;
+    int *ord[2] = {nullptr, nullptr};
+    int cur = 0;
+    int64_t col_stride = 0;
+    std::vector<HNode> nodes;
+    std::vector<int> live;         // node ids awaiting a search at the current depth
+    std::vector<char> force_exact;  // per live node: re-search sequentially
+    std::vector<SegDev> h_segs;    // segments of the live nodes (as uploaded)
+    int depth = 0;
+    u32 epoch = 0;
+    // device state of the current level
+    SegDev *d_segs = nullptr;
+    Partial *d_partials = nullptr;
+    double *d_exact_total = nullptr;
+    b200dt_candidate *d_cand = nullptr;  // single-GPU candidate buffer
+    u32 *d_own_mask = nullptr;
+    // partition plan produced by decide
+    std::vector<SegDev> plan_segs;
+    std::vector<TileDesc> plan_tiles;
+    int64_t plan_elems = 0;
+    bool exact_round_done = false;
+    // L1 leaves whose median is still to be read from the y-order column
+    std::vector<int> median_pending;
+};
+
+// ---------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) block_sum_kernel(const double *__restrict__ y, int64_t n, double *partial) {
+    __shared__ double sw[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) acc += y[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += shfl_xor_d(acc, m);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sw[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// feature-major int32 [F][stride] -> row-major int64 [N][F]
+__global__ void orders_to_rowmajor_kernel(const int *__restrict__ in, int64_t stride, int64_t N, int64_t F,
+                                          int64_t *__restrict__ out) {
+    __shared__ int tile[32][33];
+    const int64_t n0 = (int64_t)blockIdx.x * 32, f0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t f = f0 + j, n = n0 + threadIdx.x;
+        if (f < F && n < N) tile[j][threadIdx.x] = in[f * stride + n];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t n = n0 + j, f = f0 + threadIdx.x;
+        if (f < F && n < N) out[n * F + f] = (int64_t)tile[threadIdx.x][j];
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// uploads through pinned staging
+// ---------------------------------------------------------------------------------------
+enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC };
+
+template <typename T>
+static int upload(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const T *src, size_t count, T *dst) {
+    if (count == 0) return 0;
+    void *stage;
+    CKR(pinned_get(ctx, pin_slot, pin_off + count * sizeof(T), &stage));
+    memcpy((char *)stage + pin_off, src, count * sizeof(T));
+    CK(cudaMemcpyAsync(dst, (char *)stage + pin_off, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static int device_sum(b200dt_ctx *ctx, const double *d, int64_t n, double *out) {
+    double *part;
+    const int blocks = (int)std::min<int64_t>(1024, (n + 255) / 256);
+    CKR(scratch_get(ctx, SB_MISC, 1024 * 8 + 64, (void **)&part));
+    {
+        LaunchScope ls(ctx, KC_MISC, 8.0 * (double)n);
+        block_sum_kernel<<<blocks, 256, 0, ctx->stream>>>(d, n, part);
+    }
+    CK(cudaGetLastError());
+    void *stage;
+    CKR(pinned_get(ctx, PIN_MISC, 1024 * 8, &stage));
+    CK(cudaMemcpyAsync(stage, part, (size_t)blocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    for (int i = 0; i < blocks; ++i) t += ((double *)stage)[i];
+    *out = t;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------
+static void session_free(b200dt_ctx *ctx) {
+    delete ctx->session;
+    ctx->session = nullptr;
+}
+
+static int make_child(Session *s, int parent, int is_left, int start, int n, double total) {
+    HNode c;
+    c.parent = parent;
+    c.is_left = is_left;
+    c.depth = s->nodes[parent].depth + 1;
+    c.start = start;
+    c.n = n;
+    c.total = total;
+    s->nodes.push_back(c);
+    return (int)s->nodes.size() - 1;
+}
+
+static bool node_is_leaf_by_size(const Session *s, const HNode &nd) {
+    // ref one.py:40-46,145: rows <= min_sample_leaf, or depth limit
+    return nd.n <= s->min_sample_leaf || nd.depth >= s->max_depth;
+}
+
+static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F_local,
+                              int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
+                              int64_t min_sample_leaf, int variant, int64_t col_offset, int64_t F_global,
+                              const double *last_col, int64_t last_col_ld) {
+    if (N <= 0 || F_local <= 0) return ctx->fail_msg("fit: empty input");
+    if (N >= (1ll << 30)) return ctx->fail_msg("fit: N must be < 2^30");
+    if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit: max_depth out of range [0, 30]");
+    if (criterion != B200DT_L2 && criterion != B200DT_L1) return ctx->fail_msg("fit: unknown criterion");
+    session_free(ctx);
+    Session *s = new (std::nothrow) Session();
+    if (!s) return ctx->fail_msg("fit: out of host memory");
+    ctx->session = s;
+    s->N = N;
+    s->F_local = (int)F_local;
+    s->F_global = (int)F_global;
+    s->col_offset = (int)col_offset;
+    s->criterion = criterion;
+    s->max_depth = max_depth;
+    s->variant = variant;
+    s->min_improvement = min_improvement;
+    s->min_sample_leaf = min_sample_leaf;
+    const bool owns_last = (col_offset + F_local == F_global);
+    if (!owns_last && last_col == nullptr && criterion == B200DT_L2)
+        return ctx->fail_msg("fit: a rank that does not own the last global column needs last_col");
+    int F_store = (int)F_local;
+    if (!owns_last && last_col) {
+        s->total_col = F_store;
+        F_store += 1;
+    } else {
+        s->total_col = (int)F_local - 1;
+    }
+    if (criterion == B200DT_L1) {
+        s->ycol = F_store;
+        F_store += 1;
+    }
+    s->F_store = F_store;
+    s->col_stride = (N + 31) / 32 * 32;
+
+    // inputs on the device
+    if (space == B200DT_HOST) {
+        double *dX, *dy;
+        CKR(scratch_get(ctx, SB_X, (size_t)N * F_local * 8, (void **)&dX));
+        CKR(scratch_get(ctx, SB_Y, (size_t)N * 8, (void **)&dy));
+        CK(cudaMemcpy2DAsync(dX, (size_t)F_local * 8, X, (size_t)ldx * 8, (size_t)F_local * 8, (size_t)N,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        s->dX = dX;
+        s->ldx = F_local;
+        s->dy = dy;
+    } else {
+        s->dX = X;
+        s->ldx = ldx;
+        s->dy = y;
+    }
+    CKR(scratch_get(ctx, SB_ORD_A, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[0]));
+    CKR(scratch_get(ctx, SB_ORD_B, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[1]));
+    s->cur = 0;
+    // one sort per fit (one.py:139)
+    CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride));
+    if (!owns_last && last_col) {
+        const double *dl = last_col;
+        int64_t ld = last_col_ld;
+        if (space == B200DT_HOST) {
+            double *buf;
+            CKR(scratch_get(ctx, SB_LASTCOL, (size_t)N * 8, (void **)&buf));
+            CK(cudaMemcpy2DAsync(buf, 8, last_col, (size_t)last_col_ld * 8, 8, (size_t)N, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+            dl = buf;
+            ld = 1;
+        }
+        CKR(sort_columns_device(ctx, dl, N, 1, ld, s->ord[0] + (int64_t)s->total_col * s->col_stride,
+                                s->ord[1] + (int64_t)s->total_col * s->col_stride, s->col_stride));
+    }
+    if (s->ycol >= 0) {
+        CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,
+                                s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
+    }
+    // status arrays of the tiled scans: at most N/SC_TILE + (#nodes with > SC_TILE rows) tiles
+    const size_t max_tiles = (size_t)(N / SC_TILE) * 2 + 4;
+    void *p;
+    CKR(scratch_get(ctx, SB_STATUS_F, max_tiles * F_store * 4 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_STATUS_VAL, max_tiles * F_store * 16 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_STATUS_P, max_tiles * F_store * 8 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
+
+    HNode root;
+    root.start = 0;
+    root.n = (int)N;
+    CKR(device_sum(ctx, s->dy, N, &root.total));
+    s->nodes.clear();
+    s->nodes.push_back(root);
+    s->live.clear();
+    s->depth = 0;
+    if (node_is_leaf_by_size(s, s->nodes[0])) {
+        s->nodes[0].leaf = true;
+        s->nodes[0].value = root.total / (double)N;
+        if (criterion == B200DT_L1) s->median_pending.push_back(0);
+    } else {
+        s->live.push_back(0);
+    }
+    s->force_exact.assign(s->live.size(), 0);
+    return 0;
+}
+
+// Build and upload the segment table of the live nodes; returns lists of tiled / sequential nodes.
+static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tiles, std::vector<int> &small,
+                        int64_t &tile_elems, int64_t &small_elems, bool only_forced) {
+    const int n_live = (int)s->live.size();
+    s->h_segs.resize(n_live);
+    tiles.clear();
+    small.clear();
+    tile_elems = small_elems = 0;
+    int pbase = 0;
+    for (int i = 0; i < n_live; ++i) {
+        const HNode &nd = s->nodes[s->live[i]];
+        SegDev sg;
+        sg.total = nd.total;
+        sg.start = nd.start;
+        sg.n = nd.n;
+        sg.nleft = 0;
+        sg.exact = (nd.n <= EXACT_MAX_ROWS || s->force_exact[i]) ? 1 : 0;
+        sg.pbase = pbase;
+        sg.np = sg.exact ? 1 : (nd.n + SC_TILE - 1) / SC_TILE;
+        // slots are reserved as if tiled so a later forced exact re-search keeps the layout
+        pbase += (nd.n + SC_TILE - 1) / SC_TILE;
+        s->h_segs[i] = sg;
+        if (sg.exact) {
+            if (!only_forced || s->force_exact[i]) {
+                small.push_back(i);
+                small_elems += nd.n;
+            }
+        } else if (!only_forced) {
+            for (int t = 0; t < sg.np; ++t) tiles.push_back(TileDesc{i, t});
+            tile_elems += nd.n;
+        }
+    }
+    CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(SegDev) + 64, (void **)&s->d_segs));
+    CKR(scratch_get(ctx, SB_PARTIAL, (size_t)(pbase + 1) * s->F_local * sizeof(Partial) + 64, (void **)&s->d_partials));
+    CKR(scratch_get(ctx, SB_TMP2, (size_t)n_live * 8 + 64, (void **)&s->d_exact_total));
+    CKR(upload(ctx, PIN_SEARCH, 0, s->h_segs.data(), (size_t)n_live, s->d_segs));
+    return 0;
+}
+
+static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool exact_only) {
+    Session *s = ctx->session;
+    if (!s) return ctx->fail_msg("session: not begun");
+    const int n_live = (int)s->live.size();
+    if (n_live == 0) return 0;
+    for (int i = 0; i < n_live; ++i)
+        if (s->nodes[s->live[i]].n < 2)
+            return ctx->fail_msg("fit: attempt to split a node with a single row (min_sample_leaf < 1); "
+                                 "the reference raises ValueError here (argmax of an empty sequence)");
+    if (s->criterion == B200DT_L1) return l1_level_search(ctx, s, d_out, exact_only);
+    std::vector<TileDesc> tiles;
+    std::vector<int> small;
+    int64_t tile_elems, small_elems;
+    CKR(upload_level(ctx, s, tiles, small, tile_elems, small_elems, exact_only));
+    TileDesc *d_tiles;
+    int *d_list;
+    const size_t seg_bytes = (size_t)n_live * sizeof(SegDev);
+    CKR(scratch_get(ctx, SB_TILES, (tiles.size() + 1) * sizeof(TileDesc) + (small.size() + 1) * 4 + 64, (void **)&d_tiles));
+    d_list = (int *)(d_tiles + tiles.size() + 1);
+    CKR(upload(ctx, PIN_SEARCH, seg_bytes + 64, tiles.data(), tiles.size(), d_tiles));
+    CKR(upload(ctx, PIN_SEARCH, seg_bytes + 64 + (tiles.size() + 1) * sizeof(TileDesc), small.data(), small.size(), d_list));
+    LevelArgs a;
+    a.orders = s->ord[s->cur];
+    a.col_stride = s->col_stride;
+    a.F_search = s->F_local;
+    a.y = s->dy;
+    a.segs = s->d_segs;
+    a.n_segs = n_live;
+    ScanStatus st;
+    st.flag = (u32 *)ctx->scratch[SB_STATUS_F].p;
+    st.agg = (double *)ctx->scratch[SB_STATUS_VAL].p;
+    st.incl = st.agg + ((size_t)(s->N / SC_TILE) * 2 + 4) * s->F_store;
+    u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
+    s->epoch += 1;
+    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, s->epoch, ticket, s->d_partials, s->variant));
+    CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
+                        s->d_partials, s->variant));
+    CKR(launch_finalize(ctx, a, s->d_partials, s->dX, s->ldx, s->col_offset, d_out));
+    return 0;
+}
+
+// winner of one node among the ranks' candidates: (score desc, k asc, aux desc, f asc)
+static bool cand_better(const b200dt_candidate &b, const b200dt_candidate &a) {
+    if (b.k < 0) return false;
+    if (a.k < 0) return true;
+    if (b.gain != a.gain) return b.gain > a.gain;
+    if (b.k != a.k) return b.k < a.k;
+    if (b.aux != a.aux) return b.aux > a.aux;
+    return b.f < a.f;
+}
+
+static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gathered, int n_ranks, u32 *d_mask,
+                               int *need_partition, int *need_exact) {
+    Session *s = ctx->session;
+    if (!s) return ctx->fail_msg("session: not begun");
+    *need_partition = 0;
+    *need_exact = 0;
+    const int n_live = (int)s->live.size();
+    if (n_live == 0) return 0;
+    b200dt_candidate *h;
+    CKR(pinned_get(ctx, PIN_RESULT, (size_t)n_ranks * n_live * sizeof(b200dt_candidate), (void **)&h));
+    CK(cudaMemcpyAsync(h, d_gathered, (size_t)n_ranks * n_live * sizeof(b200dt_candidate), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<b200dt_candidate> win(n_live);
+    bool any_flag = false;
+    for (int i = 0; i < n_live; ++i) {
+        b200dt_candidate best = h[i];
+        double second = best.gain2;
+        for (int r = 1; r < n_ranks; ++r) {
+            const b200dt_candidate &c = h[(size_t)r * n_live + i];
+            second = std::max(second, c.gain2);
+            if (cand_better(c, best)) {
+                if (best.k >= 0) second = std::max(second, best.gain);
+                best = c;
+            } else if (c.k >= 0) {
+                second = std::max(second, c.gain);
+            }
+        }
+        win[i] = best;
+        if (best.k < 0) return ctx->fail_msg("fit: a node produced no split candidate");
+        if (!std::isfinite(best.gain)) continue;  // NaN/inf targets: nothing to disambiguate
+        // a runner-up within NEAR_TIE_EPS of the winner of an approximate (parallel-scan) search
+        if (!best.exact && second >= best.gain - NEAR_TIE_EPS * std::fabs(best.gain)) {
+            s->force_exact[i] = 1;
+            any_flag = true;
+        }
+    }
+    if (any_flag) {
+        *need_exact = 1;
+        return 0;
+    }
+    // apply: leaf or split (ref one.py:145-160)
+    std::vector<int> marks;
+    int max_left = 0;
+    std::vector<int> next_live;
+    s->plan_segs.clear();
+    s->plan_tiles.clear();
+    s->plan_elems = 0;
+    for (int i = 0; i < n_live; ++i) {
+        const int nid = s->live[i];
+        const b200dt_candidate &w = win[i];
+        double score_for_test;
+        if (s->criterion == B200DT_L1)
+            score_for_test = -w.gain;  // children cost (strategy_l1.py:158: same "<" test)
+        else if (s->variant == 1)
+            score_for_test = w.gain;
+        else
+            score_for_test = w.gain * w.gain;  // one.py:93 returns the square of the best ratio score
+        if (score_for_test < s->min_improvement) {  // one.py:150
+            HNode &nd = s->nodes[nid];
+            nd.leaf = true;
+            nd.value = nd.total / (double)nd.n;
+            if (s->criterion == B200DT_L1) s->median_pending.push_back(nid);
+            continue;
+        }
+        const int start = s->nodes[nid].start, n = s->nodes[nid].n;
+        const double total = s->nodes[nid].total;
+        const int nl = w.k + 1;
+        s->nodes[nid].feature = w.f;
+        s->nodes[nid].thr = w.threshold;
+        s->nodes[nid].value = total / (double)n;
+        const int lc = make_child(s, nid, 1, start, nl, w.left_sum);
+        const int rc = make_child(s, nid, 0, start + nl, n - nl, total - w.left_sum);
+        s->nodes[nid].left = lc;
+        s->nodes[nid].right = rc;
+        bool any_search = false;
+        for (int c : {lc, rc}) {
+            HNode &ch = s->nodes[c];
+            if (node_is_leaf_by_size(s, ch)) {
+                ch.leaf = true;
+                ch.value = ch.total / (double)ch.n;
+                if (s->criterion == B200DT_L1) s->median_pending.push_back(c);
+            } else {
+                next_live.push_back(c);
+                any_search = true;
+            }
+        }
+        // L1 leaves read their median from the partitioned y-order column, so always partition
+        if (any_search || s->criterion == B200DT_L1) {
+            SegDev sg;
+            sg.total = 0.0;
+            sg.start = start;
+            sg.n = n;
+            sg.pbase = 0;
+            sg.np = (n + SC_TILE - 1) / SC_TILE;
+            sg.nleft = nl;
+            sg.exact = 0;
+            const int si = (int)s->plan_segs.size();
+            s->plan_segs.push_back(sg);
+            for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{si, t});
+            s->plan_elems += n;
+            const int fl = w.f - s->col_offset;
+            if (fl >= 0 && fl < s->F_local) {  // this rank owns the winning column: it marks the left rows
+                marks.push_back(fl);
+                marks.push_back(start);
+                marks.push_back(w.k);
+                max_left = std::max(max_left, nl);
+            }
+        }
+    }
+    if (!s->plan_segs.empty()) {
+        *need_partition = 1;
+        CK(cudaMemsetAsync(d_mask, 0, (size_t)((s->N + 31) / 32) * 4, ctx->stream));
+        if (!marks.empty()) {
+            int *d_marks;
+            CKR(scratch_get(ctx, SB_TMP_I64, marks.size() * 4 + 64, (void **)&d_marks));
+            CKR(upload(ctx, PIN_PLAN, 0, marks.data(), marks.size(), d_marks));
+            CKR(launch_mark_left(ctx, s->ord[s->cur], s->col_stride, d_marks, (int)marks.size() / 3, max_left, d_mask));
+        }
+    }
+    s->live.swap(next_live);
+    s->force_exact.assign(s->live.size(), 0);
+    s->depth += 1;
+    return 0;
+}
+
+static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
+    Session *s = ctx->session;
+    if (!s) return ctx->fail_msg("session: not begun");
+    if (s->plan_segs.empty()) return 0;
+    SegDev *d_segs;
+    TileDesc *d_tiles;
+    const size_t seg_bytes = s->plan_segs.size() * sizeof(SegDev);
+    const size_t mark_bytes = (size_t)s->plan_segs.size() * 12 + 64;  // marks staged first in PIN_PLAN
+    CKR(scratch_get(ctx, SB_SEG, seg_bytes + 64, (void **)&d_segs));
+    CKR(scratch_get(ctx, SB_TILES, s->plan_tiles.size() * sizeof(TileDesc) + 64, (void **)&d_tiles));
+    CKR(upload(ctx, PIN_PLAN, mark_bytes, s->plan_segs.data(), s->plan_segs.size(), d_segs));
+    CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
+    u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
+    s->epoch += 1;
+    CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
+                         (int)s->plan_tiles.size(), s->plan_elems, d_mask, (u64 *)ctx->scratch[SB_STATUS_P].p,
+                         s->epoch, ticket));
+    s->cur ^= 1;
+    s->plan_segs.clear();
+    s->plan_tiles.clear();
+    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s));
+    return 0;
+}
+
+static int session_finish_impl(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
+                               double *threshold, double *value, int64_t capacity, int64_t *node_count) {
+    Session *s = ctx->session;
+    if (!s) return ctx->fail_msg("session: not begun");
+    if (!s->live.empty()) return ctx->fail_msg("session: finish called before the tree is complete");
+    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s));
+    const int64_t count = (int64_t)s->nodes.size();
+    if (count > capacity) return ctx->fail_msg("fit: tree arrays too small");
+    // pre-order ids, left first (one.py:26-31: ids are handed out as tasks are popped;
+    // one.py:157-160: right is pushed first so left is popped first)
+    std::vector<int> new_id(count, -1), stack;
+    stack.push_back(0);
+    int next = 0;
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        new_id[v] = next++;
+        if (!s->nodes[v].leaf) {
+            stack.push_back(s->nodes[v].right);
+            stack.push_back(s->nodes[v].left);
+        }
+    }
+    for (int64_t v = 0; v < count; ++v) {
+        const HNode &nd = s->nodes[v];
+        const int id = new_id[v];
+        if (nd.leaf) {
+            children_left[id] = -1;
+            children_right[id] = -1;
+            feature[id] = -2;
+            threshold[id] = -2.0;
+        } else {
+            children_left[id] = new_id[nd.left];
+            children_right[id] = new_id[nd.right];
+            feature[id] = nd.feature;
+            threshold[id] = nd.thr;
+        }
+        value[id] = nd.value;
+    }
+    *node_count = count;
+    return 0;
+}
+
+// accessors used by l1.cu
+int session_cur_orders(Session *s, const int **orders, int64_t *col_stride) {
+    *orders = s->ord[s->cur];
+    *col_stride = s->col_stride;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+static std::string g_create_error;
+
+extern "C" {
+
+int b200dt_abi_version(void) { return B200DT_ABI_VERSION; }
+
+int b200dt_create(b200dt_ctx **out, int device_id) {
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("b200dt_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); this library has no CPU fallback";
+        return 1;
+    }
+    if (device_id < 0 || device_id >= n) {
+        g_create_error = "b200dt_create: device id out of range";
+        return 1;
+    }
+    e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    b200dt_ctx *ctx = new (std::nothrow) b200dt_ctx();
+    if (!ctx) {
+        g_create_error = "out of host memory";
+        return 1;
+    }
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device_id);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        delete ctx;
+        return 1;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete ctx;
+        return 1;
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->scratch.resize(SB_COUNT);
+    *out = ctx;
+    return 0;
+}
+
+void b200dt_destroy(b200dt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_drain(ctx);
+    session_free(ctx);
+    for (auto &b : ctx->scratch)
+        if (b.p) cudaFree(b.p);
+    for (auto p : ctx->pinned)
+        if (p) cudaFreeHost(p);
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *b200dt_last_error(const b200dt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200dt_set_stream(b200dt_ctx *ctx, void *cuda_stream) {
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int b200dt_synchronize(b200dt_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dt_session_begin(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F_local, int64_t ldx,
+                         int space, int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf,
+                         int variant, int64_t col_offset, int64_t F_global, const double *last_col,
+                         int64_t last_col_ld) {
+    CK(cudaSetDevice(ctx->device));
+    return session_begin_impl(ctx, X, y, N, F_local, ldx, space, criterion, max_depth, min_improvement,
+                              min_sample_leaf, variant, col_offset, F_global, last_col, last_col_ld);
+}
+
+int b200dt_session_live(b200dt_ctx *ctx, int64_t *n_live) {
+    if (!ctx->session) return ctx->fail_msg("session: not begun");
+    *n_live = (int64_t)ctx->session->live.size();
+    return 0;
+}
+
+int b200dt_session_search(b200dt_ctx *ctx, b200dt_candidate *d_out) {
+    CK(cudaSetDevice(ctx->device));
+    return session_search_impl(ctx, d_out, false);
+}
+
+int b200dt_session_search_exact(b200dt_ctx *ctx, b200dt_candidate *d_out) {
+    CK(cudaSetDevice(ctx->device));
+    return session_search_impl(ctx, d_out, true);
+}
+
+int b200dt_session_decide(b200dt_ctx *ctx, const b200dt_candidate *d_gathered, int n_ranks, uint32_t *d_side_mask,
+                          int *need_partition, int *need_exact) {
+    CK(cudaSetDevice(ctx->device));
+    return session_decide_impl(ctx, d_gathered, n_ranks, d_side_mask, need_partition, need_exact);
+}
+
+int b200dt_session_partition(b200dt_ctx *ctx, const uint32_t *d_side_mask) {
+    CK(cudaSetDevice(ctx->device));
+    return session_partition_impl(ctx, d_side_mask);
+}
+
+int b200dt_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
+                          double *threshold, double *value, int64_t capacity, int64_t *node_count) {
+    CK(cudaSetDevice(ctx->device));
+    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, capacity, node_count);
+    session_free(ctx);
+    return r;
+}
+
+int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F, int64_t ldx, int space,
+               int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant,
+               int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
+               int64_t capacity, int64_t *node_count) {
+    CK(cudaSetDevice(ctx->device));
+    CKR(session_begin_impl(ctx, X, y, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf,
+                           variant, 0, F, nullptr, 0));
+    Session *s = ctx->session;
+    while (!s->live.empty()) {
+        const int n_live = (int)s->live.size();
+        CKR(scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(b200dt_candidate) + 64, (void **)&s->d_cand));
+        CKR(session_search_impl(ctx, s->d_cand, false));
+        int need_part = 0, need_exact = 0;
+        CKR(session_decide_impl(ctx, s->d_cand, 1, s->d_own_mask, &need_part, &need_exact));
+        if (need_exact) {
+            CKR(session_search_impl(ctx, s->d_cand, true));
+            CKR(session_decide_impl(ctx, s->d_cand, 1, s->d_own_mask, &need_part, &need_exact));
+            if (need_exact) return ctx->fail_msg("fit: exact re-search did not resolve a tie");
+        }
+        if (need_part) CKR(session_partition_impl(ctx, s->d_own_mask));
+    }
+    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, capacity, node_count);
+    session_free(ctx);
+    return r;
+}
+
+// ---- single-node ops (parity tests of K1 / K2 / K4) --------------------------------------
+int b200dt_argsort_columns(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64_t ldx, int x_space,
+                           int64_t *orders_out, int out_space) {
+    CK(cudaSetDevice(ctx->device));
+    if (N <= 0 || F <= 0) return 0;
+    const double *dX = X;
+    int64_t ld = ldx;
+    if (x_space == B200DT_HOST) {
+        double *buf;
+        CKR(scratch_get(ctx, SB_X, (size_t)N * F * 8, (void **)&buf));
+        CK(cudaMemcpy2DAsync(buf, (size_t)F * 8, X, (size_t)ldx * 8, (size_t)F * 8, (size_t)N, cudaMemcpyHostToDevice,
+                             ctx->stream));
+        dX = buf;
+        ld = F;
+    }
+    const int64_t stride = (N + 31) / 32 * 32;
+    int *a, *b;
+    CKR(scratch_get(ctx, SB_ORD_A, (size_t)F * stride * 4, (void **)&a));
+    CKR(scratch_get(ctx, SB_ORD_B, (size_t)F * stride * 4, (void **)&b));
+    CKR(sort_columns_device(ctx, dX, N, F, ld, a, b, stride));
+    int64_t *d_out = orders_out;
+    if (out_space == B200DT_HOST) CKR(scratch_get(ctx, SB_OUT, (size_t)N * F * 8, (void **)&d_out));
+    {
+        LaunchScope ls(ctx, KC_MISC, 12.0 * (double)N * F);
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)((F + 31) / 32));
+        orders_to_rowmajor_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(a, stride, N, F, d_out);
+    }
+    CK(cudaGetLastError());
+    if (out_space == B200DT_HOST)
+        CK(cudaMemcpyAsync(orders_out, d_out, (size_t)N * F * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// stage one node given as a host (n, F) int64 order matrix into a throw-away session
+static int stage_single_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const double *X,
+                             int64_t ldx, const double *y, int64_t N, int criterion, int variant) {
+    if (n <= 0 || F <= 0 || N <= 0) return ctx->fail_msg("split_node: empty input");
+    session_free(ctx);
+    Session *s = new (std::nothrow) Session();
+    if (!s) return ctx->fail_msg("out of host memory");
+    ctx->session = s;
+    s->N = N;
+    s->F_local = s->F_global = (int)F;
+    s->F_store = (int)F;
+    s->total_col = (int)F - 1;
+    s->criterion = criterion;
+    s->variant = variant;
+    s->max_depth = 1;
+    s->col_stride = (n + 31) / 32 * 32;
+    std::vector<int> h((size_t)F * s->col_stride, 0);
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t f = 0; f < F; ++f) {
+            const int64_t r = orders[i * F + f];
+            if (r < 0 || r >= N) return ctx->fail_msg("split_node: order entry out of range");
+            h[(size_t)f * s->col_stride + i] = (int)r;
+        }
+    CKR(scratch_get(ctx, SB_ORD_A, h.size() * 4, (void **)&s->ord[0]));
+    CKR(scratch_get(ctx, SB_ORD_B, h.size() * 4, (void **)&s->ord[1]));
+    CK(cudaMemcpyAsync(s->ord[0], h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    double *dX = nullptr, *dy;
+    CKR(scratch_get(ctx, SB_Y, (size_t)N * 8, (void **)&dy));
+    CK(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (X) {
+        CKR(scratch_get(ctx, SB_X, (size_t)N * F * 8, (void **)&dX));
+        CK(cudaMemcpy2DAsync(dX, (size_t)F * 8, X, (size_t)ldx * 8, (size_t)F * 8, (size_t)N, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // h goes out of scope
+    s->dX = dX;
+    s->ldx = F;
+    s->dy = dy;
+    const size_t max_tiles = (size_t)(n / SC_TILE) * 2 + 4;
+    void *p;
+    CKR(scratch_get(ctx, SB_STATUS_F, max_tiles * F * 4 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_STATUS_VAL, max_tiles * F * 16 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_STATUS_P, max_tiles * F * 8 + 64, &p, true));
+    CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
+    HNode root;
+    root.start = 0;
+    root.n = (int)n;
+    s->nodes.push_back(root);
+    s->live.push_back(0);
+    s->force_exact.assign(1, 0);
+    return 0;
+}
+
+static int single_node_search(b200dt_ctx *ctx, int64_t *out_k, int64_t *out_f, double *out_score,
+                              double *out_threshold) {
+    Session *s = ctx->session;
+    // the node total for the approximate path: sum of y over the node's rows (column 0 order)
+    {
+        // gather-sum on the host side of the staged rows is avoided: use the exact kernel's total
+        s->force_exact[0] = (s->nodes[0].n <= EXACT_MAX_ROWS) ? 1 : 0;
+    }
+    b200dt_candidate *d_c;
+    CKR(scratch_get(ctx, SB_RESULT, sizeof(b200dt_candidate) + 64, (void **)&d_c));
+    b200dt_candidate h;
+    for (int round = 0; round < 2; ++round) {
+        CKR(session_search_impl(ctx, d_c, false));
+        CK(cudaMemcpyAsync(&h, d_c, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (h.exact || !(h.gain2 >= h.gain - NEAR_TIE_EPS * std::fabs(h.gain))) break;
+        s->force_exact[0] = 1;
+    }
+    *out_k = h.k;
+    *out_f = h.f;
+    *out_score = h.gain;
+    *out_threshold = h.threshold;
+    return 0;
+}
+
+int b200dt_l2_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const double *X, int64_t ldx,
+                         const double *y, int64_t N, int variant, int64_t *out_k, int64_t *out_f, double *out_gain,
+                         double *out_threshold) {
+    CK(cudaSetDevice(ctx->device));
+    if (n < 2) return ctx->fail_msg("l2_split_node: attempt to get argmax of an empty sequence (n < 2)");
+    CKR(stage_single_node(ctx, orders, n, F, X, ldx, y, N, B200DT_L2, variant));
+    Session *s = ctx->session;
+    // approximate path needs the node total: sum y over the node's rows
+    double total = 0.0;
+    for (int64_t i = 0; i < n; ++i) total += y[orders[i * F + (F - 1)]];
+    s->nodes[0].total = total;
+    double score = 0.0;
+    int r = single_node_search(ctx, out_k, out_f, &score, out_threshold);
+    *out_gain = (variant == 1) ? score : score * score;
+    session_free(ctx);
+    return r;
+}
+
+int b200dt_l1_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const double *X, int64_t ldx,
+                         const double *y, int64_t N, int64_t *out_k, int64_t *out_f, double *out_cost,
+                         double *out_threshold) {
+    CK(cudaSetDevice(ctx->device));
+    if (n < 2) return ctx->fail_msg("l1_split_node: attempt to get argmin of an empty sequence (n < 2)");
+    CKR(stage_single_node(ctx, orders, n, F, X, ldx, y, N, B200DT_L1, 1));
+    double score = 0.0;
+    int r = single_node_search(ctx, out_k, out_f, &score, out_threshold);
+    *out_cost = -score;
+    session_free(ctx);
+    return r;
+}
+
+int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const int64_t *left_rows,
+                        int64_t n_left, int64_t n_samples, int64_t *left_out, int64_t *right_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (n_left < 0 || n_left > n) return ctx->fail_msg("split_orders: bad n_left");
+    std::vector<double> ydummy((size_t)n_samples, 0.0);
+    CKR(stage_single_node(ctx, orders, n, F, nullptr, 0, ydummy.data(), n_samples, B200DT_L2, 1));
+    Session *s = ctx->session;
+    // side mask from the explicit row list (one.py:111-112)
+    std::vector<u32> hmask((size_t)(n_samples + 31) / 32, 0u);
+    for (int64_t i = 0; i < n_left; ++i) {
+        const int64_t r = left_rows[i];
+        if (r < 0 || r >= n_samples) return ctx->fail_msg("split_orders: left row out of range");
+        hmask[r >> 5] |= 1u << (r & 31);
+    }
+    CK(cudaMemcpyAsync(s->d_own_mask, hmask.data(), hmask.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SegDev sg;
+    sg.total = 0.0;
+    sg.start = 0;
+    sg.n = (int)n;
+    sg.pbase = 0;
+    sg.np = (int)((n + SC_TILE - 1) / SC_TILE);
+    sg.nleft = (int)n_left;
+    sg.exact = 0;
+    s->plan_segs.assign(1, sg);
+    s->plan_tiles.clear();
+    for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{0, t});
+    s->plan_elems = n;
+    s->criterion = B200DT_L2;
+    CKR(session_partition_impl(ctx, s->d_own_mask));
+    std::vector<int> h((size_t)F * s->col_stride);
+    CK(cudaMemcpyAsync(h.data(), s->ord[s->cur], h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t n_right = n - n_left;
+    for (int64_t f = 0; f < F; ++f) {
+        const int *col = h.data() + (size_t)f * s->col_stride;
+        for (int64_t i = 0; i < n_left; ++i) left_out[i * F + f] = col[i];
+        for (int64_t i = 0; i < n_right; ++i) right_out[i * F + f] = col[n_left + i];
+    }
+    session_free(ctx);
+    return 0;
+}
+
+int b200dt_cummedian(b200dt_ctx *ctx, const double *a, int64_t n, int a_space, double *out, int out_space) {
+    CK(cudaSetDevice(ctx->device));
+    if (n <= 0) return 0;
+    const double *d_a = a;
+    double *d_out = out;
+    if (a_space == B200DT_HOST) {
+        double *buf;
+        CKR(scratch_get(ctx, SB_Y, (size_t)n * 8, (void **)&buf));
+        CK(cudaMemcpyAsync(buf, a, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_a = buf;
+    }
+    if (out_space == B200DT_HOST) CKR(scratch_get(ctx, SB_OUT, (size_t)n * 16, (void **)&d_out));
+    CKR(l1_cummedian_device(ctx, d_a, n, d_out));
+    if (out_space == B200DT_HOST)
+        CK(cudaMemcpyAsync(out, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dt_predict(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64_t ldx, int x_space,
+                   const int64_t *feature, const double *threshold, const int64_t *children_left,
+                   const int64_t *children_right, const double *value, int64_t n_nodes, double *out_value,
+                   int32_t *out_leaf, int out_space) {
+    CK(cudaSetDevice(ctx->device));
+    if (N <= 0) return 0;
+    if (n_nodes <= 0 || n_nodes > (1ll << 30)) return ctx->fail_msg("predict: bad node count");
+    const double *dX = X;
+    int64_t ld = ldx;
+    if (x_space == B200DT_HOST) {
+        double *buf;
+        CKR(scratch_get(ctx, SB_X, (size_t)N * F * 8, (void **)&buf));
+        CK(cudaMemcpy2DAsync(buf, (size_t)F * 8, X, (size_t)ldx * 8, (size_t)F * 8, (size_t)N, cudaMemcpyHostToDevice,
+                             ctx->stream));
+        dX = buf;
+        ld = F;
+    }
+    // tree -> device, int32 node links; longest root-to-leaf path for the traffic estimate
+    const size_t nn = (size_t)n_nodes;
+    char *stage;
+    const size_t tree_bytes = nn * (8 + 8 + 4 + 4 + 4) + 64;
+    CKR(pinned_get(ctx, PIN_MISC, tree_bytes, (void **)&stage));
+    double *h_thr = (double *)stage, *h_val = h_thr + nn;
+    int *h_feat = (int *)(h_val + nn), *h_left = h_feat + nn, *h_right = h_left + nn;
+    for (size_t i = 0; i < nn; ++i) {
+        const int64_t l = children_left[i], r = children_right[i], f = feature[i];
+        if (l < -1 || l >= n_nodes || r < -1 || r >= n_nodes) return ctx->fail_msg("predict: child id out of range");
+        if (f >= F || f < -F) return ctx->fail_msg("predict: feature index out of range");
+        h_thr[i] = threshold[i];
+        h_val[i] = value[i];
+        h_feat[i] = (int)f;
+        h_left[i] = (int)l;
+        h_right[i] = (int)r;
+    }
+    std::vector<int> depth(nn, 0);
+    double path_sum = 0.0;
+    int64_t leaves = 0;
+    for (size_t i = 0; i < nn; ++i) {  // parents precede children in both pre-order and BFS ids
+        if (h_left[i] > (int)i) depth[h_left[i]] = depth[i] + 1;
+        if (h_right[i] > (int)i) depth[h_right[i]] = depth[i] + 1;
+        if (h_left[i] == -1 && h_right[i] == -1 && (i == 0 || depth[i] > 0)) {
+            path_sum += depth[i];
+            ++leaves;
+        }
+    }
+    const double avg_path = leaves ? path_sum / (double)leaves : 0.0;
+    char *d_tree;
+    CKR(scratch_get(ctx, SB_TREE, tree_bytes, (void **)&d_tree));
+    CK(cudaMemcpyAsync(d_tree, stage, tree_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    double *d_thr = (double *)d_tree, *d_val = d_thr + nn;
+    int *d_feat = (int *)(d_val + nn), *d_left = d_feat + nn, *d_right = d_left + nn;
+    double *d_ov = out_value;
+    int *d_ol = out_leaf;
+    if (out_space == B200DT_HOST) {
+        if (out_value) CKR(scratch_get(ctx, SB_OUT, (size_t)N * 8, (void **)&d_ov));
+        if (out_leaf) CKR(scratch_get(ctx, SB_LEAF, (size_t)N * 4, (void **)&d_ol));
+    }
+    CKR(predict_device(ctx, dX, N, F, ld, d_feat, d_left, d_right, d_thr, d_val, (int)n_nodes, d_ov, d_ol, avg_path));
+    if (out_space == B200DT_HOST) {
+        if (out_value) CK(cudaMemcpyAsync(out_value, d_ov, (size_t)N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_leaf) CK(cudaMemcpyAsync(out_leaf, d_ol, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- measurement ----------------------------------------------------------------------------
+int b200dt_profile_enable(b200dt_ctx *ctx, int on) {
+    ctx->prof_on = on != 0;
+    return 0;
+}
+
+int b200dt_profile_reset(b200dt_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    prof_drain(ctx);
+    for (int i = 0; i < KC_COUNT; ++i) {
+        ctx->prof_ms[i] = 0.0;
+        ctx->prof_launches[i] = 0;
+        ctx->prof_bytes[i] = 0.0;
+    }
+    ctx->launches = 0;
+    return 0;
+}
+
+int b200dt_profile_count(void) { return KC_COUNT; }
+
+const char *b200dt_profile_name(int kc) { return (kc >= 0 && kc < KC_COUNT) ? kKernelClassNames[kc] : ""; }
+
+int b200dt_profile_get(b200dt_ctx *ctx, int kc, double *ms, int64_t *launches, double *alg_bytes) {
+    if (kc < 0 || kc >= KC_COUNT) return ctx->fail_msg("profile: bad kernel class");
+    CK(cudaSetDevice(ctx->device));
+    prof_drain(ctx);
+    *ms = ctx->prof_ms[kc];
+    *launches = ctx->prof_launches[kc];
+    *alg_bytes = ctx->prof_bytes[kc];
+    return 0;
+}
+
+int64_t b200dt_launch_count(const b200dt_ctx *ctx) { return ctx->launches; }
+
+}  // extern "C"

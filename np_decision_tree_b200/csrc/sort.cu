@@ -1,0 +1,305 @@
+// K1: per-column argsort of a row-major (N, F) float64 matrix.
+//
+// replaces np.argsort(X, axis=0)   (ref decision_tree/one.py:139, strategy_l1.py:147,177)
+//
+// Stable LSD radix sort, 8 passes of 8-bit digits over the order-preserving uint64 image of
+// each key, payload = int32 row id, every column of a batch in the same launch.
+//   prepare : X[n][f] (coalesced 64-byte row pieces) -> keys[f][n] through a shared-memory
+//             transpose, plus all 8 digit histograms per column (shared-memory atomics)
+//   pass p  : "onesweep": one read of (key, row id), one scattered write.  A tile's global
+//             digit offsets come from a decoupled look-back over the tiles before it in the
+//             same column; tiles are handed out by an atomic ticket so every predecessor of
+//             a running tile has started.
+// Algorithmic bytes per element: prepare 16; pass 0: 20; passes 1..6: 24; pass 7: 16 => 196.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr u32 RS_FLAG_AGG = 1u << 30;
+constexpr u32 RS_FLAG_INCL = 2u << 30;
+constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
+
+constexpr int PREP_COLS = 8;     // columns per prepare block: 64-byte row pieces
+constexpr int PREP_ROWS = 256;   // rows per chunk
+constexpr int PREP_PITCH = PREP_ROWS + 1;
+
+// float64 -> uint64 whose unsigned order equals the float order.
+// NaN sorts last (like numpy); -0.0 is folded onto +0.0 so the sort equals a stable argsort.
+__device__ __forceinline__ u64 sortable_key(double x) {
+    if (x != x) return ~0ull;
+    u64 b = (u64)__double_as_longlong(x);
+    if (x == 0.0) b = 0ull;
+    u64 flip = (u64)((long long)b >> 63) | 0x8000000000000000ull;
+    return b ^ flip;
+}
+
+__global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restrict__ X, int64_t N,
+                                                           int64_t ldx, int fb, u64 *__restrict__ keys,
+                                                           int64_t kstride, u32 *__restrict__ ghist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32 *hist = reinterpret_cast<u32 *>(smem_raw);                              // [8 cols][8 digits][256]
+    u64 *tile = reinterpret_cast<u64 *>(smem_raw + PREP_COLS * 8 * 256 * 4);    // [8][PREP_PITCH]
+    const int tid = threadIdx.x;
+    const int cg = blockIdx.y;
+    const int ncols = min(PREP_COLS, fb - cg * PREP_COLS);
+    for (int i = tid; i < PREP_COLS * 8 * 256; i += 256) hist[i] = 0;
+    __syncthreads();
+    const int tcol = tid & (PREP_COLS - 1);
+    const int trow = tid >> 3;  // 32 rows per sweep
+    for (int64_t chunk = blockIdx.x; chunk * PREP_ROWS < N; chunk += gridDim.x) {
+        const int64_t r0 = chunk * PREP_ROWS;
+#pragma unroll
+        for (int it = 0; it < PREP_ROWS / 32; ++it) {
+            const int rr = it * 32 + trow;
+            const int64_t r = r0 + rr;
+            if (r < N && tcol < ncols) {
+                const double x = X[r * ldx + cg * PREP_COLS + tcol];
+                const u64 k = sortable_key(x);
+                tile[tcol * PREP_PITCH + rr] = k;
+                u32 *h = hist + tcol * 8 * 256;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) atomicAdd(&h[d * 256 + (u32)((k >> (8 * d)) & 255)], 1u);
+            }
+        }
+        __syncthreads();
+        if (r0 + tid < N) {
+            for (int j = 0; j < ncols; ++j)
+                keys[(int64_t)(cg * PREP_COLS + j) * kstride + r0 + tid] = tile[j * PREP_PITCH + tid];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < ncols * 8 * 256; i += 256) {
+        const u32 c = hist[i];
+        if (c) atomicAdd(&ghist[(int64_t)cg * PREP_COLS * 8 * 256 + i], c);
+    }
+}
+
+// exclusive scan of each 256-bin histogram: one block per (column, digit)
+__global__ void __launch_bounds__(256) sort_scan_hist_kernel(const u32 *__restrict__ ghist,
+                                                             u32 *__restrict__ gbase) {
+    __shared__ u32 wsum[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 c = ghist[(int64_t)blockIdx.x * 256 + tid];
+    u32 incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    gbase[(int64_t)blockIdx.x * 256 + tid] = base + incl - c;
+}
+
+struct RsSmem {
+    u32 warp_hist[RS_WARPS][256];
+    u32 bin_start[256];
+    u32 gofs[256];
+    u32 warp_sums[RS_WARPS];
+    u32 ticket;
+    u32 pad[3];
+    u64 keys[RS_TILE];
+    int vals[RS_TILE];
+};
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(
+    const u64 *__restrict__ keys_in, const int *__restrict__ vals_in, u64 *__restrict__ keys_out,
+    int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
+    int64_t kstride, int64_t vstride, int tiles_per_col, int pass) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sm.ticket = atomicAdd(ticket_ctr, 1u);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 t = sm.ticket;
+    const int col = t / tiles_per_col, tile = t % tiles_per_col;
+    const int64_t base = (int64_t)tile * RS_TILE;
+    const int shift = pass * 8;
+    const u64 *kin = keys_in + (int64_t)col * kstride;
+    const int64_t wbase = base + warp * (32 * RS_ITEMS) + lane;
+
+    u64 key[RS_ITEMS];
+    u32 rank[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int64_t idx = wbase + i * 32;
+        key[i] = idx < N ? ld_stream_u64(kin + idx) : ~0ull;
+    }
+    // stable rank of each key among the keys of its warp with the same digit
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const bool valid = (wbase + i * 32) < N;
+        const u32 d = (u32)(key[i] >> shift) & 255u;
+        const u32 vm = __ballot_sync(FULL_MASK, valid);
+        const u32 peers = __match_any_sync(FULL_MASK, d) & vm;
+        u32 old = 0;
+        if (valid) old = sm.warp_hist[warp][d];
+        __syncwarp();
+        if (valid && lane == (u32)(__ffs(peers) - 1)) sm.warp_hist[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[i] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    // thread `tid` owns digit `tid`: exclusive offsets of the warps, tile total
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        const u32 c = sm.warp_hist[w][tid];
+        sm.warp_hist[w][tid] = run;
+        run += c;
+    }
+    const u32 total = run;
+    // decoupled look-back along the tiles of this column, one chain per digit
+    u32 *st = status + (int64_t)col * tiles_per_col * 256;
+    u32 excl = 0;
+    if (tile == 0) {
+        st_relaxed_u32(&st[tid], RS_FLAG_INCL | total);
+    } else {
+        st_relaxed_u32(&st[(int64_t)tile * 256 + tid], RS_FLAG_AGG | total);
+        int look = tile - 1;
+        while (true) {
+            const u32 s = ld_relaxed_u32(&st[(int64_t)look * 256 + tid]);
+            const u32 fl = s & ~RS_VAL_MASK;
+            if (fl == 0) continue;
+            excl += s & RS_VAL_MASK;
+            if (fl == RS_FLAG_INCL) break;
+            --look;
+        }
+        st_relaxed_u32(&st[(int64_t)tile * 256 + tid], RS_FLAG_INCL | (excl + total));
+    }
+    // tile-local start of each digit's run (block exclusive scan over the 256 digits)
+    u32 incl = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= (u32)d) incl += o;
+    }
+    if (lane == 31) sm.warp_sums[warp] = incl;
+    __syncthreads();
+    u32 wofs = 0;
+    for (int w = 0; w < warp; ++w) wofs += sm.warp_sums[w];
+    const u32 bstart = wofs + incl - total;
+    sm.bin_start[tid] = bstart;
+    sm.gofs[tid] = gbase[((int64_t)col * 8 + pass) * 256 + tid] + excl - bstart;  // mod 2^32
+    __syncthreads();
+    // reorder inside the tile so that each digit's keys leave as one contiguous run
+    const int *vin = FIRST ? nullptr : vals_in + (int64_t)col * vstride;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int64_t idx = wbase + i * 32;
+        if (idx < N) {
+            const u32 d = (u32)(key[i] >> shift) & 255u;
+            const u32 pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[i];
+            sm.keys[pos] = key[i];
+            sm.vals[pos] = FIRST ? (int)idx : ld_stream_i32(vin + idx);
+        }
+    }
+    __syncthreads();
+    const int count = (int)min((int64_t)RS_TILE, N - base);
+    u64 *kout = LAST ? nullptr : keys_out + (int64_t)col * kstride;
+    int *vout = vals_out + (int64_t)col * vstride;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int pos = j * RS_THREADS + tid;
+        if (pos < count) {
+            const u64 k = sm.keys[pos];
+            const u32 d = (u32)(k >> shift) & 255u;
+            const u32 dest = sm.gofs[d] + (u32)pos;
+            if (!LAST) kout[dest] = k;
+            vout[dest] = sm.vals[pos];
+        }
+    }
+}
+
+}  // namespace
+
+// Sort every column of dX (device, row-major, row stride ldx).  Result: d_out[f*col_stride + j]
+// = row id of the j-th smallest value of column f.  d_alt is scratch of the same shape.
+int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
+                        int *d_out, int *d_alt, int64_t col_stride) {
+    if (N <= 0 || F <= 0) return 0;
+    if (N > (int64_t)RS_VAL_MASK) return ctx->fail_msg("argsort: N must be < 2^30");
+    cudaStream_t s = ctx->stream;
+    const int tiles = (int)((N + RS_TILE - 1) / RS_TILE);
+    // column batch: bound the key double-buffer to a fraction of the free memory
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = free_b / 3;
+    const size_t cap = (size_t)24 << 30;
+    if (budget > cap) budget = cap;
+    int64_t fb_max = (int64_t)(budget / (16ull * (size_t)N));
+    fb_max = (fb_max / PREP_COLS) * PREP_COLS;
+    if (fb_max < PREP_COLS) fb_max = PREP_COLS;
+    int64_t Fb = F < fb_max ? ((F + PREP_COLS - 1) / PREP_COLS) * PREP_COLS : fb_max;
+    // reuse what is already allocated if it is big enough for a smaller batch
+    u64 *keys0, *keys1;
+    u32 *hist, *status;
+    CKR(scratch_get(ctx, SB_KEYS0, (size_t)Fb * N * 8, (void **)&keys0));
+    CKR(scratch_get(ctx, SB_KEYS1, (size_t)Fb * N * 8, (void **)&keys1));
+    CKR(scratch_get(ctx, SB_SORT_HIST, (size_t)Fb * 8 * 256 * 4 * 2, (void **)&hist));
+    const size_t status_bytes = (size_t)Fb * tiles * 256 * 4 + 16;
+    CKR(scratch_get(ctx, SB_SORT_STATUS, status_bytes, (void **)&status));
+    u32 *ghist = hist, *gbase = hist + (size_t)Fb * 8 * 256;
+
+    const size_t prep_smem = PREP_COLS * 8 * 256 * 4 + PREP_COLS * PREP_PITCH * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(sort_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_done = true;
+    }
+    for (int64_t c0 = 0; c0 < F; c0 += Fb) {
+        const int fb = (int)(F - c0 < Fb ? F - c0 : Fb);
+        const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
+        CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
+        {
+            int64_t chunks = (N + PREP_ROWS - 1) / PREP_ROWS;
+            int64_t rb = (3ll * ctx->sm_count * 2 + groups - 1) / groups;
+            if (rb > chunks) rb = chunks;
+            if (rb < 1) rb = 1;
+            LaunchScope ls(ctx, KC_SORT_PREPARE, 16.0 * (double)N * fb);
+            sort_prepare_kernel<<<dim3((unsigned)rb, groups), 256, prep_smem, s>>>(dX + c0, N, ldx, fb, keys0, N, ghist);
+        }
+        {
+            LaunchScope ls(ctx, KC_MISC, 0.0);
+            sort_scan_hist_kernel<<<fb * 8, 256, 0, s>>>(ghist, gbase);
+        }
+        CK(cudaGetLastError());
+        int *v[2] = {d_alt + c0 * col_stride, d_out + c0 * col_stride};
+        u64 *k[2] = {keys0, keys1};
+        u32 *ticket = status + (size_t)Fb * tiles * 256;
+        for (int p = 0; p < 8; ++p) {
+            CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4, s));
+            CK(cudaMemsetAsync(ticket, 0, 16, s));
+            const unsigned grid = (unsigned)((int64_t)fb * tiles);
+            const u64 *kin = k[p & 1];
+            u64 *kout = k[(p + 1) & 1];
+            const int *vin = v[(p + 1) & 1];
+            int *vout = v[p & 1];
+            const double bytes = (p == 0 ? 20.0 : p == 7 ? 16.0 : 24.0) * (double)N * fb;
+            LaunchScope ls(ctx, KC_SORT_PASS, bytes);
+            if (p == 0)
+                radix_pass_kernel<true, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
+                    kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+            else if (p == 7)
+                radix_pass_kernel<false, true><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
+                    kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+            else
+                radix_pass_kernel<false, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
+                    kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+        }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}

@@ -1,0 +1,66 @@
+"""Mirror of the reference module ``decision_tree/strategy_l1.py`` -- L1 (MAE) regression trees.
+
+Citations are to /root/reference/decision_tree/strategy_l1.py.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ._common import context_for, fit_into, matrix_arg, orders_arg
+from .one import DecisionTree, Task, split_orders  # noqa: F401  (strategy_l1.py:3)
+from .np_stream_median import cummedian  # noqa: F401  (strategy_l1.py:4)
+
+
+def best_l1_improvements_v2(ys):
+    """(row, column, children L1 cost) of the best split of ``ys`` (n, F) (strategy_l1.py:87-122).
+    The cost is minimised; ties go to the lowest row, then the lowest column."""
+    ys = np.ascontiguousarray(ys, dtype=np.float64)
+    n, F = ys.shape
+    # present ys as y[orders]: y = ys laid out column after column, orders[i, f] = f*n + i
+    y = np.ascontiguousarray(ys.T).ravel()
+    orders = (np.arange(F, dtype=np.int64)[None, :] * n + np.arange(n, dtype=np.int64)[:, None])
+    ctx = context_for()
+    k, f = ctypes.c_int64(), ctypes.c_int64()
+    cost, thr = ctypes.c_double(), ctypes.c_double()
+    ctx.check(ctx.lib.b200dt_l1_split_node(ctx.handle, orders.ctypes.data, n, F, None, 0, y.ctypes.data,
+                                           y.shape[0], ctypes.byref(k), ctypes.byref(f),
+                                           ctypes.byref(cost), ctypes.byref(thr)))
+    return k.value, f.value, cost.value
+
+
+best_l1_improvements = best_l1_improvements_v2   # strategy_l1.py:49-84: same results, pure Python there
+
+
+def greedy_regression_split_v2(orders, X, y):
+    """strategy_l1.py:134-140 -> (threshold, column, cost, left_rows)."""
+    orders = orders_arg(orders)
+    ctx = context_for()
+    xp, xs, xk, N, F, ldx = matrix_arg(X)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    k, f = ctypes.c_int64(), ctypes.c_int64()
+    cost, thr = ctypes.c_double(), ctypes.c_double()
+    ctx.check(ctx.lib.b200dt_l1_split_node(ctx.handle, orders.ctypes.data, orders.shape[0], F, xp, ldx,
+                                           y.ctypes.data, y.shape[0], ctypes.byref(k), ctypes.byref(f),
+                                           ctypes.byref(cost), ctypes.byref(thr)))
+    return thr.value, f.value, cost.value, orders[:k.value + 1, f.value]
+
+
+greedy_regression_split = greedy_regression_split_v2   # strategy_l1.py:125-131
+
+
+def build_regression_tree_v2(X, y, max_depth=2, max_feature=100, min_improvement=1e-7, min_sample_leaf=1,
+                             leaf_from_data=np.median):
+    """Fit an L1 regression tree (strategy_l1.py:173-200).  A node becomes a leaf when its best
+    children COST is below ``min_improvement`` (strategy_l1.py:188), as in the reference."""
+    if leaf_from_data is not np.median:
+        raise NotImplementedError("only leaf_from_data=np.median (the reference default) runs on the GPU")
+    tree = DecisionTree(2 ** (max_depth + 1))
+    return fit_into(tree, X, y, _lib.L1, max_depth, min_improvement, min_sample_leaf, 1).final()
+
+
+def build_regression_tree(X, y, max_depth=2, max_feature=100, min_improvement=1e-7, min_sample_leaf=1,
+                          leaf_from_data=np.median):
+    """strategy_l1.py:143-170: the pure-Python-heap twin builds the same tree; same kernel path."""
+    return build_regression_tree_v2(X, y, max_depth, max_feature, min_improvement, min_sample_leaf,
+                                    leaf_from_data)
