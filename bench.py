@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- depth-10 MSE fit throughput (rows*features/s), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one whole fit (argsort of every column + 10 levels of split search and partition +
+tree read-back) of the synthetic 10 000 000 x 256 float64 regression problem of
+BASELINE.json configs[3] (make_regression's recipe: N(0,1) features, 10 informative columns
+with coefficients 100*U(0,1), no noise).  With N > 1 the columns of the SAME problem are
+sharded over the ranks (strong scaling).
+
+  value : N*F / t, inputs resident in HBM when the timed region starts (CUDA events on the
+          launch stream, barrier + synchronize on both sides, max over ranks).
+  e2e   : the same fit through the public API with HOST (pinned) buffers -- every step copies
+          X and y host->device and the tree device->host inside the timed region.
+  roofline : the kernel class with the largest share of the step; achieved = algorithmic
+          bytes / summed CUDA-event time of its launches in the timed
+          region; peak = MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the oracle (numpy port of the reference, single thread like the reference)
+          on a bounded row sample of the same generator, rank 0, N=1 only.
+
+--impl reference times the reference's CPU algorithm (the oracle port; the Python reference
+itself cannot travel to the GPU box) on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "depth-10 MSE fit throughput"
+UNIT = "rows*features/s"
+N_INFORMATIVE = 10
+SEED = 0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--features", type=int, default=256)
+    ap.add_argument("--depth", type=int, default=10)
+    ap.add_argument("--cpu-rows", type=int, default=100_000, help="row sample of the CPU baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic problem: identical for any number of ranks (columns are generated one by one)
+# ---------------------------------------------------------------------------------------------
+def informative_columns(F):
+    rs = np.random.RandomState(SEED)
+    cols = np.sort(rs.permutation(F)[:min(N_INFORMATIVE, F)])
+    coef = 100.0 * rs.uniform(size=cols.shape[0])
+    return cols, coef
+
+
+def gen_column_torch(N, c, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED * 1_000_003 + 7919 * c + 1)
+    return torch.randn(N, dtype=torch.float64, device=device, generator=g)
+
+
+def gen_problem_torch(N, F, lo, hi, device):
+    """Columns [lo, hi) of X, the replicated y, and the global last column."""
+    import torch
+    X = torch.empty((N, hi - lo), dtype=torch.float64, device=device)
+    for c in range(lo, hi):
+        X[:, c - lo] = gen_column_torch(N, c, device)
+    cols, coef = informative_columns(F)
+    y = torch.zeros(N, dtype=torch.float64, device=device)
+    for c, w in zip(cols, coef):
+        col = X[:, c - lo] if lo <= c < hi else gen_column_torch(N, int(c), device)
+        y += w * col
+    last = None if hi == F else gen_column_torch(N, F - 1, device)
+    return X, y, last
+
+
+def gen_problem_numpy(N, F):
+    """CPU-side sample of the same recipe (numpy stream; used only for the CPU arms)."""
+    rs = np.random.RandomState(SEED + 1)
+    X = rs.standard_normal((N, F))
+    cols, coef = informative_columns(F)
+    return X, X[:, cols] @ coef
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load": samples in the upper half of what was seen (idle gaps sit at low clocks)
+        load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms (oracle port; single thread like the reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_fit_seconds(rows, F, depth, repeats=1):
+    import oracle
+    X, y = gen_problem_numpy(rows, F)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.fit_l2(X, y, max_depth=depth)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows, F = args.cpu_rows, args.features
+    import oracle
+    X, y = gen_problem_numpy(rows, F)
+    for _ in range(args.warmup):
+        oracle.fit_l2(X, y, max_depth=args.depth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.fit_l2(X, y, max_depth=args.depth)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = rows * F / dt
+    sample = f"{rows} x {F} rows sample of the same generator, whole depth-{args.depth} fit per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"L2 regression-tree fit, max_depth={args.depth}, {args.rows} x {F} f64 "
+                               f"(BASELINE.json configs[3]); CPU arm on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from np_decision_tree_b200 import _lib
+    from np_decision_tree_b200.sharded import fit_sharded, shard_columns
+    from np_decision_tree_b200.decision_tree import one
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, F, D = args.rows, args.features, args.depth
+    lo, hi = shard_columns(F, world, rank)
+    ctx = _lib.default_context(local)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    X, y, last = gen_problem_torch(N, F, lo, hi, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return fit_sharded(X, y, lo, F, last_col=last, max_depth=D, ctx=ctx)
+
+    for _ in range(max(args.warmup, 3)):
+        tree = step()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tree = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ctx.profile()
+    launches = ctx.launch_count()
+    ctx.profile_enable(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = N * F / (ms_per_step * 1e-3)
+
+    # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = measure_e2e(args, torch, dist, one, fit_sharded, ctx, X, y, last, lo, hi, world, rank, dev, barrier)
+        except Exception as ex:  # e.g. not enough host memory to pin the matrix
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": str(ex)[:200]}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernels = {}
+        for name, p in prof.items():
+            per_step_ms = p["ms"] / args.steps
+            ach = p["alg_bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 and p["alg_bytes"] > 0 else None
+            kernels[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": p["launches"] / args.steps,
+                             "share_of_step": round(per_step_ms / ms_per_step, 4),
+                             "achieved_gbs": None if ach is None else round(ach, 1),
+                             "frac": None if ach is None else round(ach / peak, 4)}
+        timed = {k: v for k, v in prof.items() if v["alg_bytes"] > 0}
+        dom = max(timed, key=lambda k: timed[k]["ms"]) if timed else None
+        roofline = None
+        if dom:
+            p = prof[dom]
+            ach = p["alg_bytes"] / (p["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                        "alg_bytes_per_launch": p["alg_bytes"] / p["launches"],
+                        "avg_launch_ms": p["ms"] / p["launches"]}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            rows = args.cpu_rows
+            secs = cpu_fit_seconds(rows, F, D)
+            cpu = {"value": rows * F / secs, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{rows} x {F} row sample of the same recipe, whole depth-{D} fit, "
+                             f"{secs:.1f} s on 1 of {os.cpu_count()} host cores (the reference is single-threaded)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"L2 regression-tree fit, max_depth={D}, {N} x {F} f64 "
+                                   "(BASELINE.json configs[3]), columns sharded over the GPUs",
+                       "rows": N, "features": F, "max_depth": D, "nodes": tree.max_node_ + 1,
+                       "l2_flush": "inputs (X %.1f GB per GPU) exceed the 126 MB L2" % (X.numel() * 8 / 1e9)},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture of this kernel, if there is one."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
+def measure_e2e(args, torch, dist, one, fit_sharded, ctx, X, y, last, lo, hi, world, rank, dev, barrier):
+    N, F, D = args.rows, args.features, args.depth
+    Fl = hi - lo
+    # host copies of this rank's inputs in pinned memory (outside the timed region)
+    hX = torch.empty((N, Fl), dtype=torch.float64, pin_memory=True)
+    hy = torch.empty(N, dtype=torch.float64, pin_memory=True)
+    hX.copy_(X)
+    hy.copy_(y)
+    hlast = None
+    if last is not None:
+        hlast = torch.empty(N, dtype=torch.float64, pin_memory=True)
+        hlast.copy_(last)
+    torch.cuda.synchronize()
+    h2d = (N * Fl + N + (N if last is not None else 0)) * 8
+    tree_bytes = (2 ** (D + 1) - 1) * 40
+    if world == 1:
+        Xn, yn = hX.numpy(), hy.numpy()
+
+        def step():
+            return one.build_regression_tree(Xn, yn, max_depth=D)   # the call a user of the reference makes
+        del X
+    else:
+        dX = torch.empty((N, Fl), dtype=torch.float64, device=dev)
+        dy = torch.empty(N, dtype=torch.float64, device=dev)
+        dl = torch.empty(N, dtype=torch.float64, device=dev) if last is not None else None
+
+        def step():
+            dX.copy_(hX, non_blocking=True)
+            dy.copy_(hy, non_blocking=True)
+            if dl is not None:
+                dl.copy_(hlast, non_blocking=True)
+            return fit_sharded(dX, dy, lo, F, last_col=dl, max_depth=D, ctx=ctx)
+    torch.cuda.empty_cache()
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        step()
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([max(e0.elapsed_time(e1) / args.e2e_steps * 1e-3, wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    return {"value": N * F / secs, "unit": UNIT, "ms_per_step": secs * 1e3, "steps": args.e2e_steps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": tree_bytes,
+            "api": "decision_tree.one.build_regression_tree(numpy X, numpy y)" if world == 1
+                   else "sharded.fit_sharded after pinned host->device copies"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

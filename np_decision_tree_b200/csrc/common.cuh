@@ -65,6 +65,9 @@ struct b200dt_ctx {
     int64_t prof_launches[KC_COUNT] = {0};
     double prof_bytes[KC_COUNT] = {0};
     int64_t launches = 0;
+    // epoch of the look-back flag words: monotonic per context because the status buffers are
+    // reused across sessions (a stale flag of an old launch must never look current)
+    u32 epoch = 0;
 
     // named grow-only scratch buffers (no allocation in steady state)
     std::vector<DevBuf> scratch;

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <initializer_list>
 #include <limits>
 #include <new>
 
@@ -55,7 +56,6 @@ struct Session {
     std::vector<char> force_exact;  // per live node: re-search sequentially
     std::vector<SegDev> h_segs;    // segments of the live nodes (as uploaded)
     int depth = 0;
-    u32 epoch = 0;
     // device state of the current level
     SegDev *d_segs = nullptr;
     Partial *d_partials = nullptr;
@@ -121,6 +121,17 @@ static int upload(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const T *src, s
     CKR(pinned_get(ctx, pin_slot, pin_off + count * sizeof(T), &stage));
     memcpy((char *)stage + pin_off, src, count * sizeof(T));
     CK(cudaMemcpyAsync(dst, (char *)stage + pin_off, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// advance the look-back epoch; on wrap-around clear every status buffer first
+static int next_epoch(b200dt_ctx *ctx) {
+    if (ctx->epoch >= (1u << 30) - 2) {
+        for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_L1_H})
+            if (ctx->scratch[id].p) CK(cudaMemsetAsync(ctx->scratch[id].p, 0, ctx->scratch[id].cap, ctx->stream));
+        ctx->epoch = 0;
+    }
+    ctx->epoch += 1;
     return 0;
 }
 
@@ -344,8 +355,8 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     st.agg = (double *)ctx->scratch[SB_STATUS_VAL].p;
     st.incl = st.agg + ((size_t)(s->N / SC_TILE) * 2 + 4) * s->F_store;
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
-    s->epoch += 1;
-    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, s->epoch, ticket, s->d_partials, s->variant));
+    CKR(next_epoch(ctx));
+    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
     CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
                         s->d_partials, s->variant));
     CKR(launch_finalize(ctx, a, s->d_partials, s->dX, s->ldx, s->col_offset, d_out));
@@ -501,10 +512,10 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     CKR(upload(ctx, PIN_PLAN, mark_bytes, s->plan_segs.data(), s->plan_segs.size(), d_segs));
     CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
-    s->epoch += 1;
+    CKR(next_epoch(ctx));
     CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
                          (int)s->plan_tiles.size(), s->plan_elems, d_mask, (u64 *)ctx->scratch[SB_STATUS_P].p,
-                         s->epoch, ticket));
+                         ctx->epoch, ticket));
     s->cur ^= 1;
     s->plan_segs.clear();
     s->plan_tiles.clear();
