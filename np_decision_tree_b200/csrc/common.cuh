@@ -105,7 +105,7 @@ enum ScratchId {
     SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
     SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
     SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
-    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_COUNT
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_COUNT
 };
 
 static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {
@@ -144,6 +144,8 @@ static inline int pinned_get(b200dt_ctx *ctx, int slot, size_t bytes, void **out
         ctx->pinned_cap.resize(slot + 1, 0);
     }
     if (ctx->pinned_cap[slot] < bytes) {
+        // an earlier async copy may still be reading the old buffer
+        CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->pinned[slot]) CK(cudaFreeHost(ctx->pinned[slot]));
         ctx->pinned[slot] = nullptr;
         size_t want = bytes * 2 + 4096;

@@ -127,7 +127,7 @@ static int upload(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const T *src, s
 // advance the look-back epoch; on wrap-around clear every status buffer first
 static int next_epoch(b200dt_ctx *ctx) {
     if (ctx->epoch >= (1u << 30) - 2) {
-        for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_L1_H})
+        for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_VAL2, SB_STATUS_P, SB_L1_H})
             if (ctx->scratch[id].p) CK(cudaMemsetAsync(ctx->scratch[id].p, 0, ctx->scratch[id].cap, ctx->stream));
         ctx->epoch = 0;
     }
@@ -256,12 +256,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,
                                 s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
     }
-    // status arrays of the tiled scans: at most N/SC_TILE + (#nodes with > SC_TILE rows) tiles
-    const size_t max_tiles = (size_t)(N / SC_TILE) * 2 + 4;
-    void *p;
-    CKR(scratch_get(ctx, SB_STATUS_F, max_tiles * F_store * 4 + 64, &p, true));
-    CKR(scratch_get(ctx, SB_STATUS_VAL, max_tiles * F_store * 16 + 64, &p, true));
-    CKR(scratch_get(ctx, SB_STATUS_P, max_tiles * F_store * 8 + 64, &p, true));
+    // (the look-back status arrays are sized per launch from the actual tile count)
     CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
 
     HNode root;
@@ -350,10 +345,13 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     a.y = s->dy;
     a.segs = s->d_segs;
     a.n_segs = n_live;
+    // look-back status: one entry per (tile, column); a freshly (re)allocated buffer is zeroed,
+    // which no epoch ever matches
     ScanStatus st;
-    st.flag = (u32 *)ctx->scratch[SB_STATUS_F].p;
-    st.agg = (double *)ctx->scratch[SB_STATUS_VAL].p;
-    st.incl = st.agg + ((size_t)(s->N / SC_TILE) * 2 + 4) * s->F_store;
+    const size_t n_status = tiles.size() * (size_t)s->F_local + 1;
+    CKR(scratch_get(ctx, SB_STATUS_F, n_status * 4, (void **)&st.flag, true));
+    CKR(scratch_get(ctx, SB_STATUS_VAL, n_status * 8, (void **)&st.agg, true));
+    CKR(scratch_get(ctx, SB_STATUS_VAL2, n_status * 8, (void **)&st.incl, true));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
     CKR(next_epoch(ctx));
     CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
@@ -512,10 +510,11 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     CKR(upload(ctx, PIN_PLAN, mark_bytes, s->plan_segs.data(), s->plan_segs.size(), d_segs));
     CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
+    u64 *pstatus;
+    CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
     CKR(next_epoch(ctx));
     CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
-                         (int)s->plan_tiles.size(), s->plan_elems, d_mask, (u64 *)ctx->scratch[SB_STATUS_P].p,
-                         ctx->epoch, ticket));
+                         (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket));
     s->cur ^= 1;
     s->plan_segs.clear();
     s->plan_tiles.clear();
@@ -795,11 +794,6 @@ static int stage_single_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, 
     s->dX = dX;
     s->ldx = F;
     s->dy = dy;
-    const size_t max_tiles = (size_t)(n / SC_TILE) * 2 + 4;
-    void *p;
-    CKR(scratch_get(ctx, SB_STATUS_F, max_tiles * F * 4 + 64, &p, true));
-    CKR(scratch_get(ctx, SB_STATUS_VAL, max_tiles * F * 16 + 64, &p, true));
-    CKR(scratch_get(ctx, SB_STATUS_P, max_tiles * F * 8 + 64, &p, true));
     CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
     HNode root;
     root.start = 0;

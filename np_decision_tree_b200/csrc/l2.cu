@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(SC_THREADS) l2_scan_kernel(LevelArgs a, const 
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 t = s_ticket;
-    const int f = t / n_tiles, ti = t % n_tiles;
+    // tile-major order (see sort.cu): in-flight blocks spread over the columns
+    const int f = t % a.F_search, ti = t / a.F_search;
     const TileDesc td = tiles[ti];
     const SegDev sg = a.segs[td.seg];
     const int off = td.tin * SC_TILE;
@@ -159,31 +160,10 @@ __global__ void __launch_bounds__(SC_THREADS) l2_scan_kernel(LevelArgs a, const 
         if (w < warp) wexcl += s_wtot[w];
         tile_total += s_wtot[w];
     }
-    // carry-in: decoupled look-back over the earlier tiles of this (node, column)
-    if (tid == 0) {
-        const int64_t idx = (int64_t)f * n_tiles + ti;
-        double excl = 0.0;
-        if (td.tin == 0) {
-            st_relaxed_f64(st.incl + idx, tile_total);
-            st_release_u32(st.flag + idx, (epoch << 2) | 2u);
-        } else {
-            st_relaxed_f64(st.agg + idx, tile_total);
-            st_release_u32(st.flag + idx, (epoch << 2) | 1u);
-            int64_t look = idx - 1;
-            while (true) {
-                const u32 fl = ld_acquire_u32(st.flag + look);
-                if ((fl >> 2) != epoch || (fl & 3u) == 0u) continue;
-                if ((fl & 3u) == 2u) {
-                    excl += ld_relaxed_f64(st.incl + look);
-                    break;
-                }
-                excl += ld_relaxed_f64(st.agg + look);
-                --look;
-            }
-            st_relaxed_f64(st.incl + idx, excl + tile_total);
-            st_release_u32(st.flag + idx, (epoch << 2) | 2u);
-        }
-        s_excl = excl;
+    // carry-in: decoupled look-back over the earlier tiles of this (node, column), by warp 0
+    if (warp == 0) {
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        if (lane == 0) s_excl = excl;
     }
     __syncthreads();
     const double offset = s_excl + (wexcl + texcl);

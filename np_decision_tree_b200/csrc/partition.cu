@@ -25,14 +25,12 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
     }
 }
 
-constexpr u64 PF_AGG = 1ull << 62;
-constexpr u64 PF_INCL = 2ull << 62;
 
 __global__ void __launch_bounds__(SC_THREADS) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                                int64_t col_stride, const SegDev *__restrict__ segs,
                                                                const TileDesc *__restrict__ tiles, int n_tiles,
                                                                const u32 *__restrict__ mask, u64 *status, u32 epoch,
-                                                               u32 *ticket) {
+                                                               u32 *ticket, int n_cols) {
     __shared__ int s_cnt[SC_ITEMS * 8];   // left count per (item row, warp), element order
     __shared__ int s_pref[SC_ITEMS * 8];
     __shared__ int s_before;
@@ -41,7 +39,7 @@ __global__ void __launch_bounds__(SC_THREADS) partition_kernel(const int *__rest
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 t = s_ticket;
-    const int f = t / n_tiles, ti = t % n_tiles;
+    const int f = t % n_cols, ti = t / n_cols;  // tile-major order (see sort.cu)
     const TileDesc td = tiles[ti];
     const SegDev sg = segs[td.seg];
     const int off = td.tin * SC_TILE;
@@ -80,27 +78,9 @@ __global__ void __launch_bounds__(SC_THREADS) partition_kernel(const int *__rest
         }
         s_pref[2 * lane] = incl - sum;
         s_pref[2 * lane + 1] = incl - sum + c0;
-        if (lane == 31) {
-            const int tile_left = incl;
-            const int64_t idx = (int64_t)f * n_tiles + ti;
-            const u64 tag = (u64)(epoch & 0x3fffffffu) << 32;
-            int before = 0;
-            if (td.tin == 0) {
-                st_relaxed_u64(status + idx, PF_INCL | tag | (u32)tile_left);
-            } else {
-                st_relaxed_u64(status + idx, PF_AGG | tag | (u32)tile_left);
-                int64_t look = idx - 1;
-                while (true) {
-                    const u64 s = ld_relaxed_u64(status + look);
-                    if ((s & 0x3fffffff00000000ull) != tag || (s >> 62) == 0) continue;
-                    before += (int)(u32)s;
-                    if ((s >> 62) == 2) break;
-                    --look;
-                }
-                st_relaxed_u64(status + idx, PF_INCL | tag | (u32)(before + tile_left));
-            }
-            s_before = before;
-        }
+        const int tile_left = __shfl_sync(FULL_MASK, incl, 31);
+        const int before = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_left, lane);
+        if (lane == 0) s_before = before;
     }
     __syncthreads();
     const int before = s_before;
@@ -142,7 +122,7 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
     if (grid > 0x7fffffffLL) return ctx->fail_msg("partition: grid too large");
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
     partition_kernel<<<(unsigned)grid, SC_THREADS, 0, ctx->stream>>>(orders_in, orders_out, col_stride, segs, tiles,
-                                                                      n_tiles, mask, status, epoch, ticket);
+                                                                      n_tiles, mask, status, epoch, ticket, F_store);
     CK(cudaGetLastError());
     return 0;
 }

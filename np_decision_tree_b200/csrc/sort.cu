@@ -109,10 +109,10 @@ struct RsSmem {
 };
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(
+__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
     const u64 *__restrict__ keys_in, const int *__restrict__ vals_in, u64 *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
-    int64_t kstride, int64_t vstride, int tiles_per_col, int pass) {
+    int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const u32 t = sm.ticket;
-    const int col = t / tiles_per_col, tile = t % tiles_per_col;
+    // tile-major order: consecutive tickets are the same tile of different columns, so the
+    // blocks in flight spread over all columns and every look-back chain stays short
+    const int col = t % n_cols, tile = t / n_cols;
     const int64_t base = (int64_t)tile * RS_TILE;
     const int shift = pass * 8;
     const u64 *kin = keys_in + (int64_t)col * kstride;
@@ -133,19 +135,24 @@ __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(
         const int64_t idx = wbase + i * 32;
         key[i] = idx < N ? ld_stream_u64(kin + idx) : ~0ull;
     }
-    // stable rank of each key among the keys of its warp with the same digit
+    // stable rank of each key among the keys of its warp with the same digit: peers by 8 ballots
+    // (one per digit bit), one shared atomic per distinct digit (its lowest lane), old count
+    // broadcast to the peers.  Items are processed in order, so counts accumulate stably.
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const bool valid = (wbase + i * 32) < N;
         const u32 d = (u32)(key[i] >> shift) & 255u;
-        const u32 vm = __ballot_sync(FULL_MASK, valid);
-        const u32 peers = __match_any_sync(FULL_MASK, d) & vm;
+        u32 peers = __ballot_sync(FULL_MASK, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const u32 m = __ballot_sync(FULL_MASK, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? m : ~m;
+        }
+        const int leader = __ffs(peers) - 1;
         u32 old = 0;
-        if (valid) old = sm.warp_hist[warp][d];
-        __syncwarp();
-        if (valid && lane == (u32)(__ffs(peers) - 1)) sm.warp_hist[warp][d] = old + __popc(peers);
-        __syncwarp();
+        if (valid && (int)lane == leader) old = atomicAdd(&sm.warp_hist[warp][d], (u32)__popc(peers));
+        old = __shfl_sync(FULL_MASK, old, leader < 0 ? 0 : leader);
         rank[i] = old + __popc(peers & lt);
     }
     __syncthreads();
@@ -291,13 +298,13 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
             LaunchScope ls(ctx, KC_SORT_PASS, bytes);
             if (p == 0)
                 radix_pass_kernel<true, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+                    kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
             else if (p == 7)
                 radix_pass_kernel<false, true><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+                    kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
             else
                 radix_pass_kernel<false, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, p);
+                    kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
         }
         CK(cudaGetLastError());
     }

@@ -40,6 +40,101 @@ struct LevelArgs {
     int n_segs;
 };
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Decoupled look-back over the earlier tiles of one (node, column) chain, run by ONE WARP.
+// Chain entries are consecutive status indices idx-tin .. idx.  Each step inspects a window
+// of 32 predecessors: it needs every entry up to the first one that already holds an
+// inclusive prefix to have at least its aggregate published, then adds them up (fixed lane
+// order).  Flags are polled with relaxed loads (no L1 invalidate per poll); one fence per
+// window orders the flag reads before the value reads.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double lookback_f64(const ScanStatus &st, int64_t idx, int tin, u32 epoch,
+                                               double tile_total, int lane) {
+    if (tin == 0) {
+        if (lane == 0) {
+            st_relaxed_f64(st.incl + idx, tile_total);
+            st_release_u32(st.flag + idx, (epoch << 2) | 2u);
+        }
+        return 0.0;
+    }
+    if (lane == 0) {
+        st_relaxed_f64(st.agg + idx, tile_total);
+        st_release_u32(st.flag + idx, (epoch << 2) | 1u);
+    }
+    double excl = 0.0;
+    int remaining = tin;
+    int64_t look = idx - 1;
+    while (true) {
+        const bool in_range = lane < remaining;
+        u32 state;
+        int first;
+        while (true) {
+            const u32 fl = in_range ? ld_relaxed_u32(st.flag + (look - lane)) : 0u;
+            state = in_range ? (((fl >> 2) == epoch) ? (fl & 3u) : 0u) : 2u;  // past the chain head: empty prefix
+            const u32 ready = __ballot_sync(FULL_MASK, state != 0u);
+            const u32 incl = __ballot_sync(FULL_MASK, state == 2u);
+            first = __ffs(incl) - 1;
+            const u32 need = first < 0 || first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+            if ((ready & need) == need) break;
+        }
+        __threadfence();
+        double v = 0.0;
+        if (in_range && (first < 0 || lane <= first))
+            v = state == 2u ? ld_relaxed_f64(st.incl + (look - lane)) : ld_relaxed_f64(st.agg + (look - lane));
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_d(v, m);
+        excl += v;
+        if (first >= 0) break;
+        look -= 32;
+        remaining -= 32;
+    }
+    if (lane == 0) {
+        st_relaxed_f64(st.incl + idx, excl + tile_total);
+        st_release_u32(st.flag + idx, (epoch << 2) | 2u);
+    }
+    return excl;
+}
+
+// Same for integer counts packed with their flag in one 64-bit word:
+// [63:62] state, [61:32] epoch, [31:0] count -- the word itself is the message, no fence needed.
+__device__ __forceinline__ int lookback_count(u64 *status, int64_t idx, int tin, u32 epoch, int tile_count, int lane) {
+    const u64 tag = (u64)(epoch & 0x3fffffffu) << 32;
+    if (tin == 0) {
+        if (lane == 0) st_relaxed_u64(status + idx, (2ull << 62) | tag | (u32)tile_count);
+        return 0;
+    }
+    if (lane == 0) st_relaxed_u64(status + idx, (1ull << 62) | tag | (u32)tile_count);
+    int excl = 0;
+    int remaining = tin;
+    int64_t look = idx - 1;
+    while (true) {
+        const bool in_range = lane < remaining;
+        u32 state;
+        int first, val;
+        while (true) {
+            const u64 w = in_range ? ld_relaxed_u64(status + (look - lane)) : 0ull;
+            state = in_range ? (((w & 0x3fffffff00000000ull) == tag) ? (u32)(w >> 62) : 0u) : 2u;
+            val = in_range ? (int)(u32)w : 0;
+            const u32 ready = __ballot_sync(FULL_MASK, state != 0u);
+            const u32 incl = __ballot_sync(FULL_MASK, state == 2u);
+            first = __ffs(incl) - 1;
+            const u32 need = first < 0 || first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+            if ((ready & need) == need) break;
+        }
+        int v = (in_range && (first < 0 || lane <= first)) ? val : 0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL_MASK, v, m);
+        excl += v;
+        if (first >= 0) break;
+        look -= 32;
+        remaining -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(status + idx, (2ull << 62) | tag | (u32)(excl + tile_count));
+    return excl;
+}
+#endif  // __CUDACC__
+
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles,
                    int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant);
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small,
