@@ -22,7 +22,7 @@ int l1_cummedian_device(b200dt_ctx *ctx, const double *d_a, int64_t n, double *d
 int l1_leaf_medians(b200dt_ctx *ctx, Session *s);
 
 // nodes with at most this many rows are searched in the reference's sequential fp64 order
-static const int EXACT_MAX_ROWS = SC_TILE;
+static const int EXACT_MAX_ROWS = EXACT_ROWS;
 // relative gap under which two candidate scores are treated as a tie to be re-searched exactly
 static const double NEAR_TIE_EPS = 1e-9;
 
@@ -296,9 +296,9 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
         sg.nleft = 0;
         sg.exact = (nd.n <= EXACT_MAX_ROWS || s->force_exact[i]) ? 1 : 0;
         sg.pbase = pbase;
-        sg.np = sg.exact ? 1 : (nd.n + SC_TILE - 1) / SC_TILE;
+        sg.np = sg.exact ? 1 : (nd.n + WT_TILE - 1) / WT_TILE;
         // slots are reserved as if tiled so a later forced exact re-search keeps the layout
-        pbase += (nd.n + SC_TILE - 1) / SC_TILE;
+        pbase += (nd.n + WT_TILE - 1) / WT_TILE;
         s->h_segs[i] = sg;
         if (sg.exact) {
             if (!only_forced || s->force_exact[i]) {
@@ -349,15 +349,17 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     // which no epoch ever matches
     ScanStatus st;
     const size_t n_status = tiles.size() * (size_t)s->F_local + 1;
-    CKR(scratch_get(ctx, SB_STATUS_F, n_status * 4, (void **)&st.flag, true));
-    CKR(scratch_get(ctx, SB_STATUS_VAL, n_status * 8, (void **)&st.agg, true));
-    CKR(scratch_get(ctx, SB_STATUS_VAL2, n_status * 8, (void **)&st.incl, true));
+    CKR(scratch_get(ctx, SB_STATUS_F, n_status * 16, (void **)&st.slot, true));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
     CKR(next_epoch(ctx));
     CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
     CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
                         s->d_partials, s->variant));
-    CKR(launch_finalize(ctx, a, s->d_partials, s->dX, s->ldx, s->col_offset, d_out));
+    int64_t max_records = 0;
+    for (const SegDev &sg : s->h_segs) max_records = std::max<int64_t>(max_records, (int64_t)sg.np * s->F_local);
+    Partial *d_sliced;
+    CKR(scratch_get(ctx, SB_L1_G, (size_t)n_live * FIN_SLICES_HOST * sizeof(Partial) + 64, (void **)&d_sliced));
+    CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out));
     return 0;
 }
 
@@ -465,7 +467,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             sg.start = start;
             sg.n = n;
             sg.pbase = 0;
-            sg.np = (n + SC_TILE - 1) / SC_TILE;
+            sg.np = (n + PT_TILE - 1) / PT_TILE;
             sg.nleft = nl;
             sg.exact = 0;
             const int si = (int)s->plan_segs.size();
@@ -880,7 +882,7 @@ int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64
     sg.start = 0;
     sg.n = (int)n;
     sg.pbase = 0;
-    sg.np = (int)((n + SC_TILE - 1) / SC_TILE);
+    sg.np = (int)((n + PT_TILE - 1) / PT_TILE);
     sg.nleft = (int)n_left;
     sg.exact = 0;
     s->plan_segs.assign(1, sg);

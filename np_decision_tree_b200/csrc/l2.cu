@@ -5,10 +5,10 @@
 //          (ref decision_tree/one.py:52-63, 81-93, 96-107)
 //
 // Two kernels share the work:
-//  * l2_scan_kernel  -- nodes with more than SC_TILE rows.  One block per (tile, column):
-//    coalesced read of 2048 row ids, gather of y, block scan, carry-in from a decoupled
+//  * l2_scan_kernel  -- nodes with more than EXACT_ROWS rows.  One WARP per (tile, column):
+//    coalesced read of 512 row ids, gather of y, warp scan, carry-in from a decoupled
 //    look-back over the earlier tiles of the same (node, column), gain at every position,
-//    block arg-max.  Single pass: 12 algorithmic bytes per (row, feature) element.  The
+//    warp arg-max.  No block barriers; persistent grid, static tile order.  Single pass: 12 algorithmic bytes per (row, feature) element.  The
 //    parallel scan rounds differently from the reference's sequential np.cumsum, so each
 //    candidate also carries the runner-up gain; a node whose two best gains are within
 //    1e-9 relative is re-searched by the exact kernel.
@@ -102,106 +102,133 @@ __device__ __forceinline__ double score_exact(double S, int kk, int n, double me
     return fabs(__dsub_rn(__dmul_rn((double)ra, S), __dmul_rn(mean, (double)rb)));          // one.py:89-90
 }
 
-constexpr int SY_PITCH = SC_TILE + SC_TILE / 8;  // skew: one pad double per 8 => conflict-free blocked reads
+// One warp owns one tile of WT_TILE sorted positions of one (node, column); warps of a persistent
+// grid take tiles in a static interleaved order (tile-major: consecutive tiles are the same
+// position range of different columns), so no block barrier and no atomic ticket is needed:
+// a tile's predecessors in its chain have smaller indices and belong to resident warps that
+// process their own tiles in increasing order.
+constexpr int SY_PITCH = WT_TILE + WT_TILE / 16;  // 1 pad double per 16: conflict-free blocked reads
 
-__global__ void __launch_bounds__(SC_THREADS) l2_scan_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
-                                                             int n_tiles, ScanStatus st, u32 epoch, u32 *ticket,
-                                                             Partial *__restrict__ partials, int variant) {
-    __shared__ double sy[SY_PITCH];
-    __shared__ double s_wtot[SC_THREADS / 32];
-    __shared__ double s_excl;
-    __shared__ u32 s_ticket;
-    __shared__ Cand s_c[SC_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 t = s_ticket;
-    // tile-major order (see sort.cu): in-flight blocks spread over the columns
-    const int f = t % a.F_search, ti = t / a.F_search;
-    const TileDesc td = tiles[ti];
-    const SegDev sg = a.segs[td.seg];
-    const int off = td.tin * SC_TILE;
-    const int cnt = min(SC_TILE, sg.n - off);
-    const int *col = a.orders + (int64_t)f * a.col_stride + sg.start + off;
-
-    // coalesced read of the row ids, gather of y, staged so each thread gets 8 consecutive values
+__global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
+                                                         int n_tiles, ScanStatus st, u32 epoch,
+                                                         Partial *__restrict__ partials, int variant) {
+    __shared__ double sy_all[8][SY_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sy = sy_all[warp];
+    const int64_t total_tiles = (int64_t)n_tiles * a.F_search;
+    const int64_t stride_tiles = (int64_t)gridDim.x * 8;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += stride_tiles) {
+        const int f = (int)(t % a.F_search), ti = (int)(t / a.F_search);
+        const TileDesc td = tiles[ti];
+        const SegDev sg = a.segs[td.seg];
+        const int off = td.tin * WT_TILE;
+        const int cnt = min(WT_TILE, sg.n - off);
+        const int *col = a.orders + (int64_t)f * a.col_stride + sg.start + off;
+        // coalesced read of the row ids, gather of y, staged so each lane gets 16 consecutive values
+        if (cnt == WT_TILE) {
+            int r[WT_ITEMS];
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i) {
-        const int e = i * SC_THREADS + tid;
-        double v = 0.0;
-        if (e < cnt) v = __ldg(a.y + ld_stream_i32(col + e));
-        sy[e + (e >> 3)] = v;
-    }
-    __syncthreads();
-    double p[SC_ITEMS];
-    {
-        const double *src = sy + tid * (SC_ITEMS + 1);
-        double run = 0.0;
+            for (int i = 0; i < WT_ITEMS; ++i) r[i] = ld_stream_i32(col + i * 32 + lane);
 #pragma unroll
-        for (int i = 0; i < SC_ITEMS; ++i) {
-            run += src[i];
-            p[i] = run;
-        }
-    }
-    // block exclusive scan of the thread totals
-    double incl = p[SC_ITEMS - 1];
+            for (int i = 0; i < WT_ITEMS; ++i) sy[i * 34 + lane + (lane >> 4)] = __ldg(a.y + r[i]);
+        } else {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double o = shfl_up_d(incl, d);
-        if (lane >= d) incl += o;
-    }
-    double texcl = shfl_up_d(incl, 1);
-    if (lane == 0) texcl = 0.0;
-    if (lane == 31) s_wtot[warp] = incl;
-    __syncthreads();
-    double wexcl = 0.0, tile_total = 0.0;
-#pragma unroll
-    for (int w = 0; w < SC_THREADS / 32; ++w) {
-        if (w < warp) wexcl += s_wtot[w];
-        tile_total += s_wtot[w];
-    }
-    // carry-in: decoupled look-back over the earlier tiles of this (node, column), by warp 0
-    if (warp == 0) {
-        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
-        if (lane == 0) s_excl = excl;
-    }
-    __syncthreads();
-    const double offset = s_excl + (wexcl + texcl);
-    const double mean = sg.total / (double)sg.n;
-    Cand best = cand_none();
-    const int e0 = tid * SC_ITEMS;
-#pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i) {
-        const int kk = off + e0 + i;
-        if (e0 + i < cnt && kk < sg.n - 1) {
-            const double S = offset + p[i];
-            double dev;
-            const double g = score_fast(S, kk, sg.n, mean, variant, dev);
-            if (g > best.g) {
-                best.g2 = best.g;
-                best.g = g;
-                best.s = S;
-                best.dev = dev;
-                best.k = kk;
-            } else if (g > best.g2) {
-                best.g2 = g;
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const int e = i * 32 + lane;
+                sy[i * 34 + lane + (lane >> 4)] = e < cnt ? __ldg(a.y + ld_stream_i32(col + e)) : 0.0;
             }
         }
-    }
-    cand_warp_reduce(best);
-    if (lane == 0) s_c[warp] = best;
-    __syncthreads();
-    if (tid == 0) {
-        Cand b = s_c[0];
-        for (int w = 1; w < SC_THREADS / 32; ++w) cand_merge(b, s_c[w]);
-        Partial out;
-        out.score = b.g;
-        out.aux = b.dev;
-        out.lsum = b.s;
-        out.score2 = b.g2;
-        out.k = b.k == 0x7fffffff ? -1 : b.k;
-        out.f = f;
-        partials[(int64_t)(sg.pbase + td.tin) * a.F_search + f] = out;
+        __syncwarp();
+        double p[WT_ITEMS];
+        {
+            const double *src = sy + lane * 17;  // element lane*16+i sits at lane*16+i + lane
+            double run = 0.0;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                run += src[i];
+                p[i] = run;
+            }
+        }
+        __syncwarp();  // sy may be overwritten by the next tile
+        double incl = p[WT_ITEMS - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = shfl_up_d(incl, d);
+            if (lane >= d) incl += o;
+        }
+        double texcl = shfl_up_d(incl, 1);
+        if (lane == 0) texcl = 0.0;
+        const double tile_total = shfl_d(incl, 31);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        const double offset = excl + texcl;
+
+        // score of every position of this lane; best and runner-up tracked branch-free
+        const int n = sg.n;
+        const double mean = sg.total / (double)n;
+        const int k0 = off + lane * WT_ITEMS;
+        double m1 = -CUDART_INF, m2 = -CUDART_INF, sbest = 0.0, dbest = 0.0;
+        int ibest = -1;
+        if (variant == 1 && n <= (1 << 24)) {
+            // gain = dev^2 / ((k+1)(n-k-1)); the denominator is advanced exactly in fp64:
+            // den(k+1) - den(k) = n - 2k - 3.  float32(k+1) is exact for n <= 2^24 (one.py:52-53)
+            double km = (double)(k0 + 1) * mean;
+            double den = (double)(k0 + 1) * (double)(n - 1 - k0);
+            double dd = (double)(n - 2 * k0 - 3);
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const double S = offset + p[i];
+                const double dev = S - km;
+                double x;  // 1/den to ~1e-12: hardware seed + one Newton step (approximate search only)
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(den));
+                x = fma(x, fma(-den, x, 1.0), x);
+                double g = dev * dev * x;
+                if (!(lane * WT_ITEMS + i < cnt && k0 + i < n - 1)) g = -CUDART_INF;
+                m2 = fmax(m2, fmin(m1, g));
+                if (g > m1) {
+                    m1 = g;
+                    sbest = S;
+                    dbest = dev;
+                    ibest = i;
+                }
+                km += mean;
+                den += dd;
+                dd -= 2.0;
+            }
+            dbest = fabs(dbest);
+        } else {
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const int kk = k0 + i;
+                const double S = offset + p[i];
+                double dev = 0.0;
+                double g = -CUDART_INF;
+                if (lane * WT_ITEMS + i < cnt && kk < n - 1) g = score_fast(S, kk, n, mean, variant, dev);
+                m2 = fmax(m2, fmin(m1, g));
+                if (g > m1) {
+                    m1 = g;
+                    sbest = S;
+                    dbest = dev;
+                    ibest = i;
+                }
+            }
+        }
+        Cand best;
+        best.g = m1;
+        best.g2 = m2;
+        best.s = sbest;
+        best.dev = dbest;
+        best.k = ibest < 0 ? 0x7fffffff : k0 + ibest;
+        cand_warp_reduce(best);
+        if (lane == 0) {
+            Partial out;
+            out.score = best.g;
+            out.aux = best.dev;
+            out.lsum = best.s;
+            out.score2 = best.g2;
+            out.k = best.k == 0x7fffffff ? -1 : best.k;
+            out.f = f;
+            partials[(int64_t)(sg.pbase + td.tin) * a.F_search + f] = out;
+        }
     }
 }
 
@@ -301,15 +328,7 @@ __device__ __forceinline__ void partial_merge(Partial &a, const Partial &b) {
     a.score2 = s2;
 }
 
-__global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partial *__restrict__ partials,
-                                                       const double *__restrict__ X, int64_t ldx, int col_offset,
-                                                       b200dt_candidate *__restrict__ out) {
-    __shared__ Partial sp[128];
-    const int seg = blockIdx.x;
-    const SegDev sg = a.segs[seg];
-    const int tid = threadIdx.x;
-    const int64_t count = (int64_t)sg.np * a.F_search;
-    const Partial *p = partials + (int64_t)sg.pbase * a.F_search;
+__device__ __forceinline__ Partial partial_none() {
     Partial b;
     b.score = -CUDART_INF;
     b.aux = 0.0;
@@ -317,7 +336,11 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
     b.score2 = -CUDART_INF;
     b.k = -1;
     b.f = 0;
-    for (int64_t r = tid; r < count; r += 128) partial_merge(b, p[r]);
+    return b;
+}
+
+__device__ __forceinline__ Partial partial_block_reduce(Partial b, Partial *sp) {
+    const int tid = threadIdx.x;
     sp[tid] = b;
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
@@ -328,8 +351,45 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
         }
         __syncthreads();
     }
+    return sp[0];
+}
+
+constexpr int FIN_SLICES = 64;  // stage-1 blocks per node with many candidates
+
+// stage 1: blockIdx.y = node, blockIdx.x = slice of that node's (tiles x columns) candidates
+__global__ void __launch_bounds__(128) finalize_slices_kernel(LevelArgs a, const Partial *__restrict__ partials,
+                                                              Partial *__restrict__ sliced) {
+    __shared__ Partial sp[128];
+    const int seg = blockIdx.y;
+    const SegDev sg = a.segs[seg];
+    const int64_t count = (int64_t)sg.np * a.F_search;
+    const Partial *p = partials + (int64_t)sg.pbase * a.F_search;
+    Partial b = partial_none();
+    for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < count; r += (int64_t)FIN_SLICES * 128)
+        partial_merge(b, p[r]);
+    b = partial_block_reduce(b, sp);
+    if (threadIdx.x == 0) sliced[(int64_t)seg * FIN_SLICES + blockIdx.x] = b;
+}
+
+// stage 2 (or the only stage when `sliced` is null): one block per node
+__global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partial *__restrict__ partials,
+                                                       const Partial *__restrict__ sliced,
+                                                       const double *__restrict__ X, int64_t ldx, int col_offset,
+                                                       b200dt_candidate *__restrict__ out) {
+    __shared__ Partial sp[128];
+    const int seg = blockIdx.x;
+    const SegDev sg = a.segs[seg];
+    const int tid = threadIdx.x;
+    int64_t count = (int64_t)sg.np * a.F_search;
+    const Partial *p = partials + (int64_t)sg.pbase * a.F_search;
+    if (sliced) {
+        count = FIN_SLICES;
+        p = sliced + (int64_t)seg * FIN_SLICES;
+    }
+    Partial b = partial_none();
+    for (int64_t r = tid; r < count; r += 128) partial_merge(b, p[r]);
+    const Partial w = partial_block_reduce(b, sp);
     if (tid == 0) {
-        const Partial w = sp[0];
         b200dt_candidate c;
         c.gain = w.score;
         c.aux = w.aux;
@@ -340,7 +400,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
         c.f = w.f + col_offset;
         c.exact = sg.exact;
         c.pad = 0;
-        if (w.k >= 0) {
+        if (w.k >= 0 && X) {
             const int row = a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
             c.threshold = X[(int64_t)row * ldx + w.f];  // one.py:104-105: a data value, not a midpoint
         }
@@ -350,14 +410,24 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
 
 }  // namespace
 
+static int persistent_grid(b200dt_ctx *ctx, const void *kernel, int threads, int64_t max_blocks) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int64_t g = (int64_t)per_sm * ctx->sm_count;
+    if (g > max_blocks) g = max_blocks;
+    return (int)(g < 1 ? 1 : g);
+}
+
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles, int64_t n_elems,
                    ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant) {
+    (void)ticket;
     if (n_tiles <= 0) return 0;
-    CK(cudaMemsetAsync(ticket, 0, 4, ctx->stream));
-    const int64_t grid = (int64_t)n_tiles * a.F_search;
-    if (grid > 0x7fffffffLL) return ctx->fail_msg("l2 scan: grid too large");
+    const int64_t total = (int64_t)n_tiles * a.F_search;
+    // every block must be resident at once (tiles wait on earlier tiles): grid <= occupancy limit
+    const int grid = persistent_grid(ctx, (const void *)l2_scan_kernel, 256, (total + 7) / 8);
     LaunchScope ls(ctx, KC_L2_SCAN, 12.0 * (double)n_elems * a.F_search);
-    l2_scan_kernel<<<(unsigned)grid, SC_THREADS, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, ticket, partials, variant);
+    l2_scan_kernel<<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials, variant);
     CK(cudaGetLastError());
     return 0;
 }
@@ -376,11 +446,17 @@ int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, 
     return 0;
 }
 
-int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, const double *X, int64_t ldx,
-                    int col_offset, b200dt_candidate *out) {
+int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, int64_t max_records,
+                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out) {
     if (a.n_segs <= 0) return 0;
+    const Partial *stage1 = nullptr;
+    if (max_records > 64 * 1024 && sliced) {
+        LaunchScope ls(ctx, KC_FINALIZE, 0.0);
+        finalize_slices_kernel<<<dim3(FIN_SLICES, a.n_segs), 128, 0, ctx->stream>>>(a, partials, sliced);
+        stage1 = sliced;
+    }
     LaunchScope ls(ctx, KC_FINALIZE, 0.0);
-    finalize_kernel<<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, X, ldx, col_offset, out);
+    finalize_kernel<<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, stage1, X, ldx, col_offset, out);
     CK(cudaGetLastError());
     return 0;
 }

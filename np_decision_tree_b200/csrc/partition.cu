@@ -4,8 +4,8 @@
 //
 // The reference builds a boolean (N,) array with the left rows set, gathers it through
 // `orders` and compacts each column with boolean indexing (stable).  Here the mask is an
-// N-bit array (L1/L2 resident), and one block per (tile, column) computes the destination
-// of 2048 row ids from ballot counts plus a decoupled look-back over the left-counts of the
+// N-bit array (L1/L2 resident), and one warp per (tile, column) computes the destination
+// of 512 row ids from ballot counts plus a decoupled look-back over the left-counts of the
 // earlier tiles of the same (node, column).  The children are the contiguous ranges
 // [start, start+nleft) and [start+nleft, start+n) of the output array, so every node of the
 // next level is again one segment shared by all columns.
@@ -26,72 +26,60 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 }
 
 
-__global__ void __launch_bounds__(SC_THREADS) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
-                                                               int64_t col_stride, const SegDev *__restrict__ segs,
-                                                               const TileDesc *__restrict__ tiles, int n_tiles,
-                                                               const u32 *__restrict__ mask, u64 *status, u32 epoch,
-                                                               u32 *ticket, int n_cols) {
-    __shared__ int s_cnt[SC_ITEMS * 8];   // left count per (item row, warp), element order
-    __shared__ int s_pref[SC_ITEMS * 8];
-    __shared__ int s_before;
-    __shared__ u32 s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 t = s_ticket;
-    const int f = t % n_cols, ti = t / n_cols;  // tile-major order (see sort.cu)
-    const TileDesc td = tiles[ti];
-    const SegDev sg = segs[td.seg];
-    const int off = td.tin * SC_TILE;
-    const int cnt = min(SC_TILE, sg.n - off);
-    const int *col = in + (int64_t)f * col_stride + sg.start + off;
+// One warp owns one tile of PT_TILE positions of one (node, column).  Every lane sees every
+// ballot, so the running left-count of the tile lives in registers: no shared memory, no
+// block barrier.  Persistent grid, static tile-major order (see l2.cu).
+__global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
+                                                           int64_t col_stride, const SegDev *__restrict__ segs,
+                                                           const TileDesc *__restrict__ tiles, int n_tiles,
+                                                           const u32 *__restrict__ mask, u64 *status, u32 epoch,
+                                                           int n_cols) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
-
-    int rows[SC_ITEMS];
-    int myrank[SC_ITEMS];
-    u32 leftbits = 0;
+    const int64_t total_tiles = (int64_t)n_tiles * n_cols;
+    const int64_t stride_tiles = (int64_t)gridDim.x * 8;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += stride_tiles) {
+        const int f = (int)(t % n_cols), ti = (int)(t / n_cols);
+        const TileDesc td = tiles[ti];
+        const SegDev sg = segs[td.seg];
+        const int off = td.tin * PT_TILE;
+        const int cnt = min(PT_TILE, sg.n - off);
+        const int *col = in + (int64_t)f * col_stride + sg.start + off;
+        int rows[PT_ITEMS];
+        if (cnt == PT_TILE) {
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i) {
-        const int e = i * SC_THREADS + tid;
-        bool is_left = false;
-        rows[i] = 0;
-        if (e < cnt) {
-            const int row = ld_stream_i32(col + e);
-            rows[i] = row;
-            is_left = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+            for (int i = 0; i < PT_ITEMS; ++i) rows[i] = ld_stream_i32(col + i * 32 + lane);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PT_ITEMS; ++i) rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
         }
-        const u32 bal = __ballot_sync(FULL_MASK, is_left);
-        if (lane == 0) s_cnt[i * 8 + warp] = __popc(bal);
-        myrank[i] = __popc(bal & lt);
-        leftbits |= (is_left ? 1u : 0u) << i;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // exclusive scan of the 64 counts (element order = item row major, warp minor)
-        const int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
-        const int sum = c0 + c1;
-        int incl = sum;
+        u32 leftbits = 0;  // bit i: item i of this lane goes left
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(FULL_MASK, incl, d);
-            if (lane >= d) incl += o;
+        for (int i = 0; i < PT_ITEMS; ++i) {
+            const int row = rows[i];
+            const bool is_left = row >= 0 && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
+            leftbits |= (is_left ? 1u : 0u) << i;
         }
-        s_pref[2 * lane] = incl - sum;
-        s_pref[2 * lane + 1] = incl - sum + c0;
-        const int tile_left = __shfl_sync(FULL_MASK, incl, 31);
-        const int before = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_left, lane);
-        if (lane == 0) s_before = before;
-    }
-    __syncthreads();
-    const int before = s_before;
-    int *ocol = out + (int64_t)f * col_stride + sg.start;
+        // ballots of the item rows; every lane sees all of them, so the tile's left count and the
+        // left rows before each item row are register arithmetic (same value in every lane)
+        int run = 0;
+        u32 bal[PT_ITEMS];
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i) {
-        const int e = i * SC_THREADS + tid;
-        if (e < cnt) {
-            const int lb = before + s_pref[i * 8 + warp] + myrank[i];  // left rows before this element
-            const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
-            ocol[dest] = rows[i];
+        for (int i = 0; i < PT_ITEMS; ++i) {
+            bal[i] = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
+            run += __popc(bal[i]);
+        }
+        int lb_row = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, run, lane);
+        int *ocol = out + (int64_t)f * col_stride + sg.start;
+#pragma unroll
+        for (int i = 0; i < PT_ITEMS; ++i) {
+            const int e = i * 32 + lane;
+            if (e < cnt) {
+                const int lb = lb_row + __popc(bal[i] & lt);  // left rows before this element
+                const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
+                ocol[dest] = rows[i];
+            }
+            lb_row += __popc(bal[i]);
         }
     }
 }
@@ -116,13 +104,17 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                      u64 *status, u32 epoch, u32 *ticket) {
+    (void)ticket;
     if (n_tiles <= 0) return 0;
-    CK(cudaMemsetAsync(ticket, 0, 4, ctx->stream));
-    const int64_t grid = (int64_t)n_tiles * F_store;
-    if (grid > 0x7fffffffLL) return ctx->fail_msg("partition: grid too large");
+    const int64_t total = (int64_t)n_tiles * F_store;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_kernel, 256, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
+    if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
-    partition_kernel<<<(unsigned)grid, SC_THREADS, 0, ctx->stream>>>(orders_in, orders_out, col_stride, segs, tiles,
-                                                                      n_tiles, mask, status, epoch, ticket, F_store);
+    partition_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, col_stride, segs, tiles, n_tiles,
+                                                              mask, status, epoch, F_store);
     CK(cudaGetLastError());
     return 0;
 }

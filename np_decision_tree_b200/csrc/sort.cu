@@ -135,23 +135,24 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
         const int64_t idx = wbase + i * 32;
         key[i] = idx < N ? ld_stream_u64(kin + idx) : ~0ull;
     }
-    // stable rank of each key among the keys of its warp with the same digit: peers by 8 ballots
-    // (one per digit bit), one shared atomic per distinct digit (its lowest lane), old count
-    // broadcast to the peers.  Items are processed in order, so counts accumulate stably.
+    // stable rank of each key among the keys of its warp with the same digit.  All 16 peer masks
+    // first (independent match.any's pipeline), then, item by item, one shared atomic per distinct
+    // digit by its lowest lane, whose old count is broadcast to the peers; items are issued in
+    // order, so the per-digit counts accumulate in the stable order.
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const bool valid = (wbase + i * 32) < N;
         const u32 d = (u32)(key[i] >> shift) & 255u;
-        u32 peers = __ballot_sync(FULL_MASK, valid);
+        rank[i] = __match_any_sync(FULL_MASK, d) & __ballot_sync(FULL_MASK, valid);
+    }
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const u32 m = __ballot_sync(FULL_MASK, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? m : ~m;
-        }
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const u32 peers = rank[i];
+        const u32 d = (u32)(key[i] >> shift) & 255u;
         const int leader = __ffs(peers) - 1;
         u32 old = 0;
-        if (valid && (int)lane == leader) old = atomicAdd(&sm.warp_hist[warp][d], (u32)__popc(peers));
+        if ((int)lane == leader && ((peers >> lane) & 1u)) old = atomicAdd(&sm.warp_hist[warp][d], (u32)__popc(peers));
         old = __shfl_sync(FULL_MASK, old, leader < 0 ? 0 : leader);
         rank[i] = old + __popc(peers & lt);
     }

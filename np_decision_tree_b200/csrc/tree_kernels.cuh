@@ -2,9 +2,12 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
-constexpr int SC_TILE = SC_THREADS * SC_ITEMS;  // 2048 sorted positions per tile
+// Tiles are owned by single warps (no block barriers anywhere in K2 / K4):
+constexpr int WT_ITEMS = 16;
+constexpr int WT_TILE = 32 * WT_ITEMS;   // K2: 512 sorted positions per warp tile
+constexpr int PT_ITEMS = 16;
+constexpr int PT_TILE = 32 * PT_ITEMS;   // K4: 512 sorted positions per warp tile
+constexpr int EXACT_ROWS = 2048;         // nodes up to this size take the sequential-order search
 
 // One node of the current level = one contiguous segment [start, start+n) of every column of
 // the order arrays.
@@ -26,9 +29,10 @@ struct TileDesc {
 // Look-back state of the tiled scans.  flag word = (epoch << 2) | state, state 1 = aggregate
 // published, 2 = inclusive prefix published; epochs make clearing between launches unnecessary.
 struct ScanStatus {
-    u32 *flag;
-    double *agg;
-    double *incl;
+    // one 16-byte slot per (tile, column): word j = [63:34] epoch, [33:32] state, [31:0] half j of the
+    // fp64 value.  A slot is valid when both words carry the current epoch and the SAME state, so a
+    // reader needs no fence and a torn read (aggregate half + inclusive half) is simply retried.
+    u64 *slot;
 };
 
 struct LevelArgs {
@@ -46,22 +50,33 @@ struct LevelArgs {
 // Chain entries are consecutive status indices idx-tin .. idx.  Each step inspects a window
 // of 32 predecessors: it needs every entry up to the first one that already holds an
 // inclusive prefix to have at least its aggregate published, then adds them up (fixed lane
-// order).  Flags are polled with relaxed loads (no L1 invalidate per poll); one fence per
-// window orders the flag reads before the value reads.
+// order).  Slots are self-validating 16-byte records polled with relaxed loads: no fences.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void status_publish(u64 *slot, u32 epoch, u32 state, double v) {
+    const u64 bits = (u64)__double_as_longlong(v);
+    const u64 tag = ((u64)epoch << 34) | ((u64)state << 32);
+    // one 16-byte store; each half is self-describing, so ordering between them does not matter
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(tag | (bits & 0xffffffffull)),
+                 "l"(tag | (bits >> 32))
+                 : "memory");
+}
+
+// state of a slot for this epoch (0 = not ready / torn) and its value
+__device__ __forceinline__ u32 status_read(const u64 *slot, u32 epoch, double &v) {
+    u64 w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    const u32 t0 = (u32)(w0 >> 32), t1 = (u32)(w1 >> 32);
+    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return (t0 == t1 && (t0 >> 2) == epoch) ? (t0 & 3u) : 0u;
+}
+
 __device__ __forceinline__ double lookback_f64(const ScanStatus &st, int64_t idx, int tin, u32 epoch,
                                                double tile_total, int lane) {
     if (tin == 0) {
-        if (lane == 0) {
-            st_relaxed_f64(st.incl + idx, tile_total);
-            st_release_u32(st.flag + idx, (epoch << 2) | 2u);
-        }
+        if (lane == 0) status_publish(st.slot + 2 * idx, epoch, 2u, tile_total);
         return 0.0;
     }
-    if (lane == 0) {
-        st_relaxed_f64(st.agg + idx, tile_total);
-        st_release_u32(st.flag + idx, (epoch << 2) | 1u);
-    }
+    if (lane == 0) status_publish(st.slot + 2 * idx, epoch, 1u, tile_total);
     double excl = 0.0;
     int remaining = tin;
     int64_t look = idx - 1;
@@ -69,19 +84,18 @@ __device__ __forceinline__ double lookback_f64(const ScanStatus &st, int64_t idx
         const bool in_range = lane < remaining;
         u32 state;
         int first;
+        double val = 0.0;
         while (true) {
-            const u32 fl = in_range ? ld_relaxed_u32(st.flag + (look - lane)) : 0u;
-            state = in_range ? (((fl >> 2) == epoch) ? (fl & 3u) : 0u) : 2u;  // past the chain head: empty prefix
+            state = 2u;  // past the chain head: empty prefix
+            val = 0.0;
+            if (in_range) state = status_read(st.slot + 2 * (look - lane), epoch, val);
             const u32 ready = __ballot_sync(FULL_MASK, state != 0u);
             const u32 incl = __ballot_sync(FULL_MASK, state == 2u);
             first = __ffs(incl) - 1;
             const u32 need = first < 0 || first == 31 ? 0xffffffffu : ((2u << first) - 1u);
             if ((ready & need) == need) break;
         }
-        __threadfence();
-        double v = 0.0;
-        if (in_range && (first < 0 || lane <= first))
-            v = state == 2u ? ld_relaxed_f64(st.incl + (look - lane)) : ld_relaxed_f64(st.agg + (look - lane));
+        double v = (in_range && (first < 0 || lane <= first)) ? val : 0.0;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_d(v, m);
         excl += v;
@@ -89,10 +103,7 @@ __device__ __forceinline__ double lookback_f64(const ScanStatus &st, int64_t idx
         look -= 32;
         remaining -= 32;
     }
-    if (lane == 0) {
-        st_relaxed_f64(st.incl + idx, excl + tile_total);
-        st_release_u32(st.flag + idx, (epoch << 2) | 2u);
-    }
+    if (lane == 0) status_publish(st.slot + 2 * idx, epoch, 2u, excl + tile_total);
     return excl;
 }
 
@@ -139,8 +150,9 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
                    int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant);
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small,
                     int64_t n_elems, int total_col, double *exact_total, Partial *partials, int variant);
-int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, const double *X,
-                    int64_t ldx, int col_offset, b200dt_candidate *out);
+constexpr int FIN_SLICES_HOST = 64;  // == FIN_SLICES in l2.cu
+int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, int64_t max_records,
+                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out);
 int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, const int *marks /* [n][3]: f,start,k */,
                      int n_marks, int max_left, u32 *mask);
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,

@@ -64,6 +64,9 @@ def inference(data, clf):
 
 
 def inference_leaf(data, clf):
-    """Leaf id per row (utils.py:34-48), int32 like the reference."""
+    """Leaf id per row (utils.py:34-48); int64 like the reference (int32 for a root-only tree)."""
     _, out, root_only = _traverse(data, clf, False, True)
-    return out[:1] if root_only else out
+    if root_only:
+        return out[:1]          # the reference's np.zeros(1, dtype=np.int32) (utils.py:37)
+    # the reference's node ids become int64 after the first np.where with the int64 child arrays
+    return out.astype(np.int64) if isinstance(out, np.ndarray) else out.long()
