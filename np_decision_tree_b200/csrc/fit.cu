@@ -12,64 +12,19 @@
 #include <limits>
 #include <new>
 
-#include "tree_kernels.cuh"
+#include "session.cuh"
 
 int predict_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx, const int *d_feature,
                    const int *d_left, const int *d_right, const double *d_threshold, const double *d_value,
                    int n_nodes, double *d_out_value, int *d_out_leaf, double avg_path_hint);
 int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool exact_only);
 int l1_cummedian_device(b200dt_ctx *ctx, const double *d_a, int64_t n, double *d_out);
-int l1_leaf_medians(b200dt_ctx *ctx, Session *s);
+int l1_leaf_medians(b200dt_ctx *ctx, Session *s, std::vector<int> &pending);
 
 // nodes with at most this many rows are searched in the reference's sequential fp64 order
 static const int EXACT_MAX_ROWS = EXACT_ROWS;
 // relative gap under which two candidate scores are treated as a tie to be re-searched exactly
 static const double NEAR_TIE_EPS = 1e-9;
-
-struct HNode {
-    int parent = -1;
-    int is_left = 1;
-    int depth = 0;
-    int start = 0;
-    int n = 0;
-    double total = 0.0;
-    int feature = -2;
-    double thr = -2.0;
-    int left = -1, right = -1;
-    double value = 0.0;
-    bool leaf = false;
-};
-
-struct Session {
-    int64_t N = 0;
-    int F_local = 0, F_store = 0, F_global = 0, col_offset = 0, total_col = 0, ycol = -1;
-    int criterion = B200DT_L2, max_depth = 0, variant = 1;
-    double min_improvement = 0.0;
-    int64_t min_sample_leaf = 1;
-    const double *dX = nullptr, *dy = nullptr;
-    int64_t ldx = 0;
-    int *ord[2] = {nullptr, nullptr};
-    int cur = 0;
-    int64_t col_stride = 0;
-    std::vector<HNode> nodes;
-    std::vector<int> live;         // node ids awaiting a search at the current depth
-    std::vector<char> force_exact;  // per live node: re-search sequentially
-    std::vector<SegDev> h_segs;    // segments of the live nodes (as uploaded)
-    int depth = 0;
-    // device state of the current level
-    SegDev *d_segs = nullptr;
-    Partial *d_partials = nullptr;
-    double *d_exact_total = nullptr;
-    b200dt_candidate *d_cand = nullptr;  // single-GPU candidate buffer
-    u32 *d_own_mask = nullptr;
-    // partition plan produced by decide
-    std::vector<SegDev> plan_segs;
-    std::vector<TileDesc> plan_tiles;
-    int64_t plan_elems = 0;
-    bool exact_round_done = false;
-    // L1 leaves whose median is still to be read from the y-order column
-    std::vector<int> median_pending;
-};
 
 // ---------------------------------------------------------------------------------------
 // small helper kernels
@@ -112,7 +67,6 @@ __global__ void orders_to_rowmajor_kernel(const int *__restrict__ in, int64_t st
 // ---------------------------------------------------------------------------------------
 // uploads through pinned staging
 // ---------------------------------------------------------------------------------------
-enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC };
 
 template <typename T>
 static int upload(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const T *src, size_t count, T *dst) {
@@ -270,7 +224,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     if (node_is_leaf_by_size(s, s->nodes[0])) {
         s->nodes[0].leaf = true;
         s->nodes[0].value = root.total / (double)N;
-        if (criterion == B200DT_L1) s->median_pending.push_back(0);
+        if (criterion == B200DT_L1) s->median_pending_cur.push_back(0);
     } else {
         s->live.push_back(0);
     }
@@ -435,7 +389,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             HNode &nd = s->nodes[nid];
             nd.leaf = true;
             nd.value = nd.total / (double)nd.n;
-            if (s->criterion == B200DT_L1) s->median_pending.push_back(nid);
+            if (s->criterion == B200DT_L1) s->median_pending_cur.push_back(nid);
             continue;
         }
         const int start = s->nodes[nid].start, n = s->nodes[nid].n;
@@ -454,7 +408,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             if (node_is_leaf_by_size(s, ch)) {
                 ch.leaf = true;
                 ch.value = ch.total / (double)ch.n;
-                if (s->criterion == B200DT_L1) s->median_pending.push_back(c);
+                if (s->criterion == B200DT_L1) s->median_pending_next.push_back(c);
             } else {
                 next_live.push_back(c);
                 any_search = true;
@@ -503,6 +457,8 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     if (s->plan_segs.empty()) return 0;
+    // L1: unsplit leaves of this level are only valid in the current buffer -- read them first
+    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s, s->median_pending_cur));
     SegDev *d_segs;
     TileDesc *d_tiles;
     const size_t seg_bytes = s->plan_segs.size() * sizeof(SegDev);
@@ -520,7 +476,7 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     s->cur ^= 1;
     s->plan_segs.clear();
     s->plan_tiles.clear();
-    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s));
+    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s, s->median_pending_next));
     return 0;
 }
 
@@ -529,7 +485,11 @@ static int session_finish_impl(b200dt_ctx *ctx, int64_t *children_left, int64_t 
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     if (!s->live.empty()) return ctx->fail_msg("session: finish called before the tree is complete");
-    if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s));
+    if (s->criterion == B200DT_L1) {
+        // no partition followed the last decisions: everything pending lives in the current buffer
+        CKR(l1_leaf_medians(ctx, s, s->median_pending_cur));
+        CKR(l1_leaf_medians(ctx, s, s->median_pending_next));
+    }
     const int64_t count = (int64_t)s->nodes.size();
     if (count > capacity) return ctx->fail_msg("fit: tree arrays too small");
     // pre-order ids, left first (one.py:26-31: ids are handed out as tasks are popped;
@@ -774,13 +734,22 @@ static int stage_single_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, 
     s->variant = variant;
     s->max_depth = 1;
     s->col_stride = (n + 31) / 32 * 32;
-    std::vector<int> h((size_t)F * s->col_stride, 0);
+    if (criterion == B200DT_L1) {  // extra column: the node's rows sorted by y (see l1.cu)
+        s->ycol = (int)F;
+        s->F_store = (int)F + 1;
+    }
+    std::vector<int> h((size_t)s->F_store * s->col_stride, 0);
     for (int64_t i = 0; i < n; ++i)
         for (int64_t f = 0; f < F; ++f) {
             const int64_t r = orders[i * F + f];
             if (r < 0 || r >= N) return ctx->fail_msg("split_node: order entry out of range");
             h[(size_t)f * s->col_stride + i] = (int)r;
         }
+    if (criterion == B200DT_L1) {
+        int *yc = h.data() + (size_t)F * s->col_stride;
+        for (int64_t i = 0; i < n; ++i) yc[i] = h[i];
+        std::stable_sort(yc, yc + n, [&](int a, int b) { return y[a] < y[b]; });
+    }
     CKR(scratch_get(ctx, SB_ORD_A, h.size() * 4, (void **)&s->ord[0]));
     CKR(scratch_get(ctx, SB_ORD_B, h.size() * 4, (void **)&s->ord[1]));
     CK(cudaMemcpyAsync(s->ord[0], h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -1,0 +1,54 @@
+// Host-side state of one tree-growing session (shared by fit.cu and l1.cu).
+#pragma once
+#include <vector>
+
+#include "tree_kernels.cuh"
+
+struct HNode {
+    int parent = -1;
+    int is_left = 1;
+    int depth = 0;
+    int start = 0;
+    int n = 0;
+    double total = 0.0;
+    int feature = -2;
+    double thr = -2.0;
+    int left = -1, right = -1;
+    double value = 0.0;
+    bool leaf = false;
+};
+
+struct Session {
+    int64_t N = 0;
+    int F_local = 0, F_store = 0, F_global = 0, col_offset = 0, total_col = 0, ycol = -1;
+    int criterion = B200DT_L2, max_depth = 0, variant = 1;
+    double min_improvement = 0.0;
+    int64_t min_sample_leaf = 1;
+    const double *dX = nullptr, *dy = nullptr;
+    int64_t ldx = 0;
+    int *ord[2] = {nullptr, nullptr};
+    int cur = 0;
+    int64_t col_stride = 0;
+    std::vector<HNode> nodes;
+    std::vector<int> live;         // node ids awaiting a search at the current depth
+    std::vector<char> force_exact;  // per live node: re-search sequentially
+    std::vector<SegDev> h_segs;    // segments of the live nodes (as uploaded)
+    int depth = 0;
+    // device state of the current level
+    SegDev *d_segs = nullptr;
+    Partial *d_partials = nullptr;
+    double *d_exact_total = nullptr;
+    b200dt_candidate *d_cand = nullptr;  // single-GPU candidate buffer
+    u32 *d_own_mask = nullptr;
+    // partition plan produced by decide
+    std::vector<SegDev> plan_segs;
+    std::vector<TileDesc> plan_tiles;
+    int64_t plan_elems = 0;
+    bool exact_round_done = false;
+    // L1 leaves whose median is still to be read from the y-order column: those that live in the
+    // current order buffer (unsplit nodes) and those created by the partition being applied
+    std::vector<int> median_pending_cur, median_pending_next;
+};
+
+
+enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1 };
