@@ -42,7 +42,8 @@ int b200dt_abi_version(void);
 int b200dt_create(b200dt_ctx **out, int device_id);
 void b200dt_destroy(b200dt_ctx *ctx);
 const char *b200dt_last_error(const b200dt_ctx *ctx);
-/* Launch on this cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+/* Launch on this cudaStream_t (e.g. torch's current stream) instead of the context's own
+ * non-blocking stream.  NULL is CUDA's legacy default stream; (void*)-1 selects the own stream. */
 int b200dt_set_stream(b200dt_ctx *ctx, void *cuda_stream);
 int b200dt_synchronize(b200dt_ctx *ctx);
 
@@ -115,7 +116,9 @@ int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int
  * last_col_ld (the reference reads the node total in that column's order, one.py:57);
  * NULL when the rank owns that column. */
 typedef struct b200dt_candidate {
-    double gain;      /* L2: variance gain (maximised); L1: children cost (minimised) */
+    double gain;      /* the score the search MAXIMISES: L2 v==1: variance gain (one.py:61);
+                         L2 v!=1: the un-squared ratio score (its square is the gain, one.py:93);
+                         L1: minus the children cost (strategy_l1.py:119)                   */
     double aux;       /* L2: |S - (k+1)*mean| of the candidate (in-row tie rule)        */
     double left_sum;  /* L2: sum of y over the left rows                               */
     double gain2;     /* best score among the OTHER local candidates (near-tie check)  */

@@ -132,7 +132,9 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream):
-        self.check(self.lib.b200dt_set_stream(self.handle, c_vp(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t handle (0 = legacy default stream), or None for the context's own."""
+        handle = c_vp(-1) if cuda_stream is None else c_vp(int(cuda_stream))
+        self.check(self.lib.b200dt_set_stream(self.handle, handle))
 
     def synchronize(self):
         self.check(self.lib.b200dt_synchronize(self.handle))

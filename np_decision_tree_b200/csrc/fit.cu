@@ -604,7 +604,9 @@ void b200dt_destroy(b200dt_ctx *ctx) {
 const char *b200dt_last_error(const b200dt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int b200dt_set_stream(b200dt_ctx *ctx, void *cuda_stream) {
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    // NULL is CUDA's legacy default stream (what torch.cuda.current_stream() is unless the caller
+    // switched streams); (void*)-1 selects the context's own non-blocking stream again
+    ctx->stream = cuda_stream == (void *)-1 ? ctx->own_stream : (cudaStream_t)cuda_stream;
     return 0;
 }
 

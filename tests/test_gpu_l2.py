@@ -191,8 +191,9 @@ def test_fit_torch_cuda_inputs(dt):
     Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
     t_dev = dt.one.build_regression_tree(Xd, yd, max_depth=6)
     assert_same_tree(t_dev, t_host, leaf_rtol=1e-12)
-    p = dt.utils.inference(Xd, t_dev)
-    assert p.is_cuda and np.array_equal(p.cpu().numpy(), dt.utils.inference(X, t_host))
+    p = dt.utils.inference(Xd, t_dev)     # device in, device out; same tree => same bits as the host path
+    assert p.is_cuda and np.array_equal(p.cpu().numpy(), dt.utils.inference(X, t_dev))
+    np.testing.assert_allclose(p.cpu().numpy(), dt.utils.inference(X, t_host), rtol=1e-12)
 
 
 # ---- K5 ------------------------------------------------------------------------------------------
