@@ -15,8 +15,11 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
+#ifndef RS_THREADS_DEF
+#define RS_THREADS_DEF 256
+#endif
+constexpr int RS_THREADS = RS_THREADS_DEF;
+constexpr int RS_ITEMS = 4096 / RS_THREADS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_AGG = 1u << 30;
@@ -52,13 +55,19 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
     const int trow = tid >> 3;  // 32 rows per sweep
     for (int64_t chunk = blockIdx.x; chunk * PREP_ROWS < N; chunk += gridDim.x) {
         const int64_t r0 = chunk * PREP_ROWS;
+        // all 8 loads of this thread first (the smem atomics below would otherwise serialise them)
+        double xv[PREP_ROWS / 32];
+#pragma unroll
+        for (int it = 0; it < PREP_ROWS / 32; ++it) {
+            const int64_t r = r0 + it * 32 + trow;
+            xv[it] = (r < N && tcol < ncols) ? X[r * ldx + cg * PREP_COLS + tcol] : 0.0;
+        }
 #pragma unroll
         for (int it = 0; it < PREP_ROWS / 32; ++it) {
             const int rr = it * 32 + trow;
             const int64_t r = r0 + rr;
             if (r < N && tcol < ncols) {
-                const double x = X[r * ldx + cg * PREP_COLS + tcol];
-                const u64 k = sortable_key(x);
+                const u64 k = sortable_key(xv[it]);
                 tile[tcol * PREP_PITCH + rr] = k;
                 u32 *h = hist + tcol * 8 * 256;
 #pragma unroll
@@ -99,9 +108,8 @@ __global__ void __launch_bounds__(256) sort_scan_hist_kernel(const u32 *__restri
 
 struct RsSmem {
     u32 warp_hist[RS_WARPS][256];
-    u32 bin_start[256];
     u32 gofs[256];
-    u32 warp_sums[RS_WARPS];
+    u32 warp_sums[8];
     u32 ticket;
     u32 pad[3];
     u64 keys[RS_TILE];
@@ -124,104 +132,125 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
     // blocks in flight spread over all columns and every look-back chain stays short
     const int col = t % n_cols, tile = t / n_cols;
     const int64_t base = (int64_t)tile * RS_TILE;
+    const int count = (int)min((int64_t)RS_TILE, N - base);
+    const bool full = count == RS_TILE;
     const int shift = pass * 8;
-    const u64 *kin = keys_in + (int64_t)col * kstride;
-    const int64_t wbase = base + warp * (32 * RS_ITEMS) + lane;
+    // everything below indexes with 32-bit tile-local offsets from these bases
+    const u64 *kin = keys_in + (int64_t)col * kstride + base;
+    const int *vin = FIRST ? nullptr : vals_in + (int64_t)col * vstride + base;
+    const int o0 = warp * (32 * RS_ITEMS) + lane;  // this lane's item 0; item i is o0 + 32 i
 
     u64 key[RS_ITEMS];
-    u32 rank[RS_ITEMS];
+    int val[RS_ITEMS];
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const int64_t idx = wbase + i * 32;
-        key[i] = idx < N ? ld_stream_u64(kin + idx) : ~0ull;
+        for (int i = 0; i < RS_ITEMS; ++i) key[i] = ld_stream_u64(kin + o0 + i * 32);
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) val[i] = FIRST ? (int)base + o0 + i * 32 : ld_stream_i32(vin + o0 + i * 32);
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const bool v = o0 + i * 32 < count;
+            key[i] = v ? ld_stream_u64(kin + o0 + i * 32) : ~0ull;
+            val[i] = FIRST ? (int)base + o0 + i * 32 : (v ? ld_stream_i32(vin + o0 + i * 32) : 0);
+        }
     }
-    // stable rank of each key among the keys of its warp with the same digit.  All 16 peer masks
+    // stable rank of each key among the keys of its warp with the same digit.  All peer masks
     // first (independent match.any's pipeline), then, item by item, one shared atomic per distinct
     // digit by its lowest lane, whose old count is broadcast to the peers; items are issued in
     // order, so the per-digit counts accumulate in the stable order.
     const u32 lt = lanemask_lt();
+    u32 rank[RS_ITEMS];
+#define RS_DIGIT(i) ((u32)(key[i] >> shift) & 255u)
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const bool valid = (wbase + i * 32) < N;
-        const u32 d = (u32)(key[i] >> shift) & 255u;
-        rank[i] = __match_any_sync(FULL_MASK, d) & __ballot_sync(FULL_MASK, valid);
+        rank[i] = __match_any_sync(FULL_MASK, RS_DIGIT(i));
+        if (!full) rank[i] &= __ballot_sync(FULL_MASK, o0 + i * 32 < count);
     }
+    u32 *my_hist = sm.warp_hist[warp];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const u32 peers = rank[i];
-        const u32 d = (u32)(key[i] >> shift) & 255u;
-        const int leader = __ffs(peers) - 1;
+        const u32 below = peers & lt;
         u32 old = 0;
-        if ((int)lane == leader && ((peers >> lane) & 1u)) old = atomicAdd(&sm.warp_hist[warp][d], (u32)__popc(peers));
-        old = __shfl_sync(FULL_MASK, old, leader < 0 ? 0 : leader);
-        rank[i] = old + __popc(peers & lt);
+        if (below == 0u && ((peers >> lane) & 1u)) old = atomicAdd(&my_hist[RS_DIGIT(i)], (u32)__popc(peers));
+        old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
+        rank[i] = old + __popc(below);
     }
     __syncthreads();
-    // thread `tid` owns digit `tid`: exclusive offsets of the warps, tile total
-    u32 run = 0;
+    if (tid < 256) {
+        // thread `tid` owns digit `tid`: exclusive offsets of the warps, tile total
+        u32 run = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-        const u32 c = sm.warp_hist[w][tid];
-        sm.warp_hist[w][tid] = run;
-        run += c;
-    }
-    const u32 total = run;
-    // decoupled look-back along the tiles of this column, one chain per digit
-    u32 *st = status + (int64_t)col * tiles_per_col * 256;
-    u32 excl = 0;
-    if (tile == 0) {
-        st_relaxed_u32(&st[tid], RS_FLAG_INCL | total);
-    } else {
-        st_relaxed_u32(&st[(int64_t)tile * 256 + tid], RS_FLAG_AGG | total);
-        int look = tile - 1;
-        while (true) {
-            const u32 s = ld_relaxed_u32(&st[(int64_t)look * 256 + tid]);
-            const u32 fl = s & ~RS_VAL_MASK;
-            if (fl == 0) continue;
-            excl += s & RS_VAL_MASK;
-            if (fl == RS_FLAG_INCL) break;
-            --look;
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const u32 c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = run;
+            run += c;
         }
-        st_relaxed_u32(&st[(int64_t)tile * 256 + tid], RS_FLAG_INCL | (excl + total));
-    }
-    // tile-local start of each digit's run (block exclusive scan over the 256 digits)
-    u32 incl = total;
+        const u32 total = run;
+        // decoupled look-back along the tiles of this column, one chain per digit
+        u32 *st = status + ((int64_t)col * tiles_per_col) * 256 + tid;
+        u32 excl = 0;
+        if (tile == 0) {
+            st_relaxed_u32(st, RS_FLAG_INCL | total);
+        } else {
+            st_relaxed_u32(st + tile * 256, RS_FLAG_AGG | total);
+            int look = tile - 1;
+            while (true) {
+                const u32 sv = ld_relaxed_u32(st + look * 256);
+                const u32 fl = sv & ~RS_VAL_MASK;
+                if (fl == 0) continue;
+                excl += sv & RS_VAL_MASK;
+                if (fl == RS_FLAG_INCL) break;
+                --look;
+            }
+            st_relaxed_u32(st + tile * 256, RS_FLAG_INCL | (excl + total));
+        }
+        // tile-local start of each digit's run (exclusive scan over the 256 digits by 8 warps)
+        u32 incl = total;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 o = __shfl_up_sync(FULL_MASK, incl, d);
-        if (lane >= (u32)d) incl += o;
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 o = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        asm volatile("bar.sync 1, 256;");  // only the 8 digit warps
+        u32 wofs = 0;
+        for (int w = 0; w < warp; ++w) wofs += sm.warp_sums[w];
+        const u32 bstart = wofs + incl - total;
+        // fold the digit's start into the warp offsets: a key's slot is warp_hist[w][d] + rank
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) sm.warp_hist[w][tid] += bstart;
+        sm.gofs[tid] = gbase[((int64_t)col * 8 + pass) * 256 + tid] + excl - bstart;  // mod 2^32
     }
-    if (lane == 31) sm.warp_sums[warp] = incl;
-    __syncthreads();
-    u32 wofs = 0;
-    for (int w = 0; w < warp; ++w) wofs += sm.warp_sums[w];
-    const u32 bstart = wofs + incl - total;
-    sm.bin_start[tid] = bstart;
-    sm.gofs[tid] = gbase[((int64_t)col * 8 + pass) * 256 + tid] + excl - bstart;  // mod 2^32
     __syncthreads();
     // reorder inside the tile so that each digit's keys leave as one contiguous run
-    const int *vin = FIRST ? nullptr : vals_in + (int64_t)col * vstride;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const int64_t idx = wbase + i * 32;
-        if (idx < N) {
-            const u32 d = (u32)(key[i] >> shift) & 255u;
-            const u32 pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[i];
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const u32 pos = my_hist[RS_DIGIT(i)] + rank[i];
             sm.keys[pos] = key[i];
-            sm.vals[pos] = FIRST ? (int)idx : ld_stream_i32(vin + idx);
+            sm.vals[pos] = val[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            if (o0 + i * 32 < count) {
+                const u32 pos = my_hist[RS_DIGIT(i)] + rank[i];
+                sm.keys[pos] = key[i];
+                sm.vals[pos] = val[i];
+            }
         }
     }
     __syncthreads();
-    const int count = (int)min((int64_t)RS_TILE, N - base);
     u64 *kout = LAST ? nullptr : keys_out + (int64_t)col * kstride;
     int *vout = vals_out + (int64_t)col * vstride;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         const int pos = j * RS_THREADS + tid;
-        if (pos < count) {
+        if (full || pos < count) {
             const u64 k = sm.keys[pos];
-            const u32 d = (u32)(k >> shift) & 255u;
-            const u32 dest = sm.gofs[d] + (u32)pos;
+            const u32 dest = sm.gofs[(u32)(k >> shift) & 255u] + (u32)pos;
             if (!LAST) kout[dest] = k;
             vout[dest] = sm.vals[pos];
         }
