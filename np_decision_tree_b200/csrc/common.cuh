@@ -30,13 +30,15 @@ enum KernelClass {
     KC_L1_DESCENT,        // one bit level of the prefix/suffix median descent
     KC_L1_COST,           // L1 cost scans + argmin
     KC_MISC,              // small helpers (histogram scan, reductions, layout converts)
+    KC_LEVEL_FUSED,       // fused per-level partition + search of the children (streaming y payload)
+    KC_PAYLOAD,           // y payload gather, once after the sort
     KC_COUNT
 };
 
 static const char *const kKernelClassNames[KC_COUNT] = {
     "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
     "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
-    "misc"};
+    "misc", "level_fused_partition_search", "gather_y_payload"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -105,7 +107,7 @@ enum ScratchId {
     SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
     SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
     SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
-    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_COUNT
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_COUNT
 };
 
 static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {
@@ -294,4 +296,5 @@ struct Partial {
 
 // cross-file entry points (host side)
 int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
-                        int *d_orders_out, int *d_orders_alt, int64_t col_stride);
+                        int *d_orders_out, int *d_orders_alt, int64_t col_stride, u64 *ext_keys0 = nullptr,
+                        u64 *ext_keys1 = nullptr, int64_t ext_key_capacity = 0);

@@ -7,6 +7,7 @@
 // are renumbered to the reference's pre-order at the end (one.py:26-31,157-160).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <limits>
@@ -190,8 +191,22 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     CKR(scratch_get(ctx, SB_ORD_A, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[0]));
     CKR(scratch_get(ctx, SB_ORD_B, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[1]));
     s->cur = 0;
+    u64 *k0 = nullptr, *k1 = nullptr;
+    int64_t kcap = 0;
+    {
+        const char *e = getenv("B200DT_FUSE");
+        s->fuse_levels = e && e[0] == '1';
+    }
+    if (criterion == B200DT_L2) {
+        // y-payload double buffer; idle during the sort, so it doubles as the radix key scratch
+        kcap = (int64_t)F_store * s->col_stride;
+        CKR(scratch_get(ctx, SB_YPAY0, (size_t)kcap * 8, (void **)&s->ypay[0]));
+        CKR(scratch_get(ctx, SB_YPAY1, (size_t)kcap * 8, (void **)&s->ypay[1]));
+        k0 = (u64 *)s->ypay[0];
+        k1 = (u64 *)s->ypay[1];
+    }
     // one sort per fit (one.py:139)
-    CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride));
+    CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
     if (!owns_last && last_col) {
         const double *dl = last_col;
         int64_t ld = last_col_ld;
@@ -204,12 +219,13 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
             ld = 1;
         }
         CKR(sort_columns_device(ctx, dl, N, 1, ld, s->ord[0] + (int64_t)s->total_col * s->col_stride,
-                                s->ord[1] + (int64_t)s->total_col * s->col_stride, s->col_stride));
+                                s->ord[1] + (int64_t)s->total_col * s->col_stride, s->col_stride, k0, k1, kcap));
     }
     if (s->ycol >= 0) {
         CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,
                                 s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
     }
+    if (s->ypay[0]) CKR(launch_gather_payload(ctx, s->ord[0], s->dy, s->ypay[0], s->col_stride, F_store, N));
     // (the look-back status arrays are sized per launch from the actual tile count)
     CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
 
@@ -240,32 +256,45 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     tiles.clear();
     small.clear();
     tile_elems = small_elems = 0;
-    int pbase = 0;
+    // candidate slots: [0, fused_slots) were written by the fused level kernel of the parents; behind
+    // them every live node reserves slots of its own (its tiles when it must be scanned here -- the
+    // root, or any node of a gather-path session -- else one, for the sequential search)
+    int pbase = s->fused_slots;
     for (int i = 0; i < n_live; ++i) {
         const HNode &nd = s->nodes[s->live[i]];
+        const int ntiles = (nd.n + WT_TILE - 1) / WT_TILE;
         SegDev sg;
         sg.total = nd.total;
         sg.start = nd.start;
         sg.n = nd.n;
         sg.nleft = 0;
         sg.exact = (nd.n <= EXACT_MAX_ROWS || s->force_exact[i]) ? 1 : 0;
+        sg.pstep = 1;
+        sg.pside = 0;
         sg.pbase = pbase;
-        sg.np = sg.exact ? 1 : (nd.n + WT_TILE - 1) / WT_TILE;
-        // slots are reserved as if tiled so a later forced exact re-search keeps the layout
-        pbase += (nd.n + WT_TILE - 1) / WT_TILE;
+        sg.np = sg.exact ? 1 : ntiles;
+        const bool from_parent = nd.has_fused && !sg.exact;
+        if (from_parent) {
+            sg.pbase = nd.fp_base;
+            sg.np = nd.fp_np;
+            sg.pstep = 2;
+            sg.pside = nd.fp_side;
+        }
+        pbase += nd.has_fused ? 1 : ntiles;
         s->h_segs[i] = sg;
         if (sg.exact) {
             if (!only_forced || s->force_exact[i]) {
                 small.push_back(i);
                 small_elems += nd.n;
             }
-        } else if (!only_forced) {
+        } else if (!only_forced && !from_parent) {
             for (int t = 0; t < sg.np; ++t) tiles.push_back(TileDesc{i, t});
             tile_elems += nd.n;
         }
     }
     CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(SegDev) + 64, (void **)&s->d_segs));
     CKR(scratch_get(ctx, SB_PARTIAL, (size_t)(pbase + 1) * s->F_local * sizeof(Partial) + 64, (void **)&s->d_partials));
+    s->next_partial_slots = 0;
     CKR(scratch_get(ctx, SB_TMP2, (size_t)n_live * 8 + 64, (void **)&s->d_exact_total));
     CKR(upload(ctx, PIN_SEARCH, 0, s->h_segs.data(), (size_t)n_live, s->d_segs));
     return 0;
@@ -297,6 +326,7 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     a.col_stride = s->col_stride;
     a.F_search = s->F_local;
     a.y = s->dy;
+    a.ypay = s->ypay[s->cur];
     a.segs = s->d_segs;
     a.n_segs = n_live;
     // look-back status: one entry per (tile, column); a freshly (re)allocated buffer is zeroed,
@@ -373,8 +403,11 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     int max_left = 0;
     std::vector<int> next_live;
     s->plan_segs.clear();
+    s->plan_fused.clear();
     s->plan_tiles.clear();
     s->plan_elems = 0;
+    s->next_fused_slots = 0;
+    const bool payload = s->ypay[0] != nullptr && s->fuse_levels;
     for (int i = 0; i < n_live; ++i) {
         const int nid = s->live[i];
         const b200dt_candidate &w = win[i];
@@ -424,10 +457,35 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             sg.np = (n + PT_TILE - 1) / PT_TILE;
             sg.nleft = nl;
             sg.exact = 0;
+            sg.pstep = 1;
+            sg.pside = 0;
             const int si = (int)s->plan_segs.size();
             s->plan_segs.push_back(sg);
             for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{si, t});
             s->plan_elems += n;
+            if (payload) {
+                // the fused level kernel scores the children that the next level searches by scan
+                PlanSeg ps;
+                ps.total_l = w.left_sum;
+                ps.total_r = total - w.left_sum;
+                ps.start = start;
+                ps.n = n;
+                ps.nleft = nl;
+                ps.fbase = s->next_fused_slots;
+                ps.score_l = ps.score_r = 0;
+                for (int c : {lc, rc}) {
+                    HNode &ch = s->nodes[c];
+                    if (!ch.leaf && ch.n > EXACT_MAX_ROWS) {
+                        ch.has_fused = true;
+                        ch.fp_base = ps.fbase;
+                        ch.fp_np = sg.np;
+                        ch.fp_side = c == lc ? 0 : 1;
+                        (c == lc ? ps.score_l : ps.score_r) = 1;
+                    }
+                }
+                s->next_fused_slots += 2 * sg.np;
+                s->plan_fused.push_back(ps);
+            }
             const int fl = w.f - s->col_offset;
             if (fl >= 0 && fl < s->F_local) {  // this rank owns the winning column: it marks the left rows
                 marks.push_back(fl);
@@ -447,6 +505,15 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             CKR(launch_mark_left(ctx, s->ord[s->cur], s->col_stride, d_marks, (int)marks.size() / 3, max_left, d_mask));
         }
     }
+    // candidate slots the next level needs: the fused ones + each live node's own reserve (this must
+    // be allocated BEFORE the fused kernel writes, and not grow afterwards)
+    size_t slots = (size_t)s->next_fused_slots + 1;
+    for (int c : next_live) {
+        const HNode &ch = s->nodes[c];
+        slots += ch.has_fused ? 1 : (size_t)(ch.n + WT_TILE - 1) / WT_TILE;
+    }
+    s->next_partial_slots = slots;
+    s->fused_slots = s->next_fused_slots;
     s->live.swap(next_live);
     s->force_exact.assign(s->live.size(), 0);
     s->depth += 1;
@@ -469,12 +536,30 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
     u64 *pstatus;
-    CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
-    CKR(next_epoch(ctx));
-    CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
-                         (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket));
+    if (s->ypay[0] && s->fuse_levels && s->plan_fused.size() == s->plan_segs.size()) {
+        // streaming path: partition (row, y) and search the children in the same pass
+        PlanSeg *d_plan;
+        const size_t plan_bytes = s->plan_fused.size() * sizeof(PlanSeg);
+        CKR(scratch_get(ctx, SB_PLAN, plan_bytes + 64, (void **)&d_plan));
+        CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64 + s->plan_tiles.size() * sizeof(TileDesc) + 64,
+                   s->plan_fused.data(), s->plan_fused.size(), d_plan));
+        CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 48, (void **)&pstatus, true));
+        CKR(scratch_get(ctx, SB_PARTIAL, (s->next_partial_slots + 1) * s->F_local * sizeof(Partial) + 64,
+                        (void **)&s->d_partials));
+        CKR(next_epoch(ctx));
+        CKR(launch_level_fused(ctx, s->ord[s->cur], s->ypay[s->cur], s->ord[s->cur ^ 1], s->ypay[s->cur ^ 1],
+                               s->col_stride, s->F_store, s->F_local, d_plan, d_tiles, (int)s->plan_tiles.size(),
+                               s->plan_elems, d_mask, pstatus, ctx->epoch, s->d_partials, s->variant));
+    } else {
+        CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
+        CKR(next_epoch(ctx));
+        CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
+                             (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket,
+                             s->ypay[s->cur], s->ypay[s->cur ^ 1]));
+    }
     s->cur ^= 1;
     s->plan_segs.clear();
+    s->plan_fused.clear();
     s->plan_tiles.clear();
     if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s, s->median_pending_next));
     return 0;
@@ -856,6 +941,8 @@ int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64
     sg.np = (int)((n + PT_TILE - 1) / PT_TILE);
     sg.nleft = (int)n_left;
     sg.exact = 0;
+    sg.pstep = 1;
+    sg.pside = 0;
     s->plan_segs.assign(1, sg);
     s->plan_tiles.clear();
     for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{0, t});

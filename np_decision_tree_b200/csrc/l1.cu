@@ -324,6 +324,8 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
         sg.np = 1;
         sg.nleft = 0;
         sg.exact = 1;
+        sg.pstep = 1;
+        sg.pside = 0;
         s->h_segs[i] = sg;
         max_n = std::max(max_n, nd.n);
         n_elems += nd.n;
@@ -377,6 +379,7 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
     a.col_stride = stride;
     a.F_search = F;
     a.y = s->dy;
+    a.ypay = nullptr;
     a.segs = s->d_segs;
     a.n_segs = n_live;
     CKR(launch_finalize(ctx, a, s->d_partials, F, nullptr, s->dX, s->ldx, s->col_offset, d_out));

@@ -16,98 +16,10 @@
 //    adds y in sorted order ONE ELEMENT AT A TIME in fp64 (shuffle broadcast), with the
 //    reference's exact operation order and no FMA contraction, so bit-exact gain ties
 //    between features resolve exactly as in the reference (hard part 1).
-#include <math_constants.h>
-
-#include "tree_kernels.cuh"
+#include "l2_score.cuh"
 
 namespace {
 
-struct Cand {
-    double g;    // score (maximised)
-    double g2;   // best score among the other candidates merged so far
-    double s;    // prefix sum at k
-    double dev;  // |S - (k+1) mean|
-    int k;
-};
-
-__device__ __forceinline__ Cand cand_none() {
-    Cand c;
-    c.g = -CUDART_INF;
-    c.g2 = -CUDART_INF;
-    c.s = 0.0;
-    c.dev = 0.0;
-    c.k = 0x7fffffff;
-    return c;
-}
-
-// same column: higher score wins, then lower position (ref one.py:62)
-__device__ __forceinline__ void cand_merge(Cand &a, const Cand &b) {
-    const bool b_wins = (b.g > a.g) || (b.g == a.g && b.k < a.k);
-    const double loser = b_wins ? a.g : b.g;
-    const double g2 = fmax(fmax(a.g2, b.g2), loser);
-    if (b_wins) {
-        a.g = b.g;
-        a.s = b.s;
-        a.dev = b.dev;
-        a.k = b.k;
-    }
-    a.g2 = g2;
-}
-
-__device__ __forceinline__ Cand cand_shfl_xor(const Cand &c, int m) {
-    Cand o;
-    o.g = shfl_xor_d(c.g, m);
-    o.g2 = shfl_xor_d(c.g2, m);
-    o.s = shfl_xor_d(c.s, m);
-    o.dev = shfl_xor_d(c.dev, m);
-    o.k = __shfl_xor_sync(FULL_MASK, c.k, m);
-    return o;
-}
-
-__device__ __forceinline__ void cand_warp_reduce(Cand &c) {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        Cand o = cand_shfl_xor(c, m);
-        cand_merge(c, o);
-    }
-}
-
-// ---- approximate (parallel-scan) score at position kk of a node with n rows ------------
-__device__ __forceinline__ double score_fast(double S, int kk, int n, double mean, int variant, double &dev) {
-    if (variant == 1) {
-        // ref one.py:57-61: w[k] * (S - (k+1) mean)^2, w = 1 / (float32(k+1) * (n-k-1))
-        dev = fabs(S - (double)(kk + 1) * mean);
-        const double ab = (double)__int2float_rn(kk + 1) * (double)(n - 1 - kk);
-        return dev * dev * rcp_fast(ab);
-    }
-    // ref one.py:85-90: |sqrt(1/(l r)) S - mean sqrt(l/r)| with float32 ratios
-    const float lc = __int2float_rn(kk + 1), rc = __int2float_rn(n - 1 - kk);
-    const float ra = __fsqrt_rn(__frcp_rn(__fmul_rn(lc, rc)));
-    const float rb = __fsqrt_rn(__fdiv_rn(lc, rc));
-    dev = 0.0;
-    return fabs((double)ra * S - mean * (double)rb);
-}
-
-// ---- reference-order score (no contraction, IEEE division) ------------------------------
-__device__ __forceinline__ double score_exact(double S, int kk, int n, double mean, int variant, double &dev) {
-    if (variant == 1) {
-        dev = fabs(__dsub_rn(S, __dmul_rn((double)(kk + 1), mean)));                       // one.py:57-58
-        const double w = __ddiv_rn(1.0, __dmul_rn((double)__int2float_rn(kk + 1), (double)(n - 1 - kk)));  // one.py:52-53
-        return __dmul_rn(w, __dmul_rn(dev, dev));                                            // one.py:61
-    }
-    const float lc = __int2float_rn(kk + 1), rc = __int2float_rn(n - 1 - kk);
-    const float ra = __fsqrt_rn(__frcp_rn(__fmul_rn(lc, rc)));                               // one.py:85-86
-    const float rb = __fsqrt_rn(__fdiv_rn(lc, rc));                                          // one.py:87-88
-    dev = 0.0;
-    return fabs(__dsub_rn(__dmul_rn((double)ra, S), __dmul_rn(mean, (double)rb)));          // one.py:89-90
-}
-
-// One warp owns one tile of WT_TILE sorted positions of one (node, column); warps of a persistent
-// grid take tiles in a static interleaved order (tile-major: consecutive tiles are the same
-// position range of different columns), so no block barrier and no atomic ticket is needed:
-// a tile's predecessors in its chain have smaller indices and belong to resident warps that
-// process their own tiles in increasing order.
-constexpr int SY_PITCH = WT_TILE + WT_TILE / 16;  // 1 pad double per 16: conflict-free blocked reads
 
 __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
                                                          int n_tiles, ScanStatus st, u32 epoch,
@@ -124,8 +36,16 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
         const int off = td.tin * WT_TILE;
         const int cnt = min(WT_TILE, sg.n - off);
         const int *col = a.orders + (int64_t)f * a.col_stride + sg.start + off;
-        // coalesced read of the row ids, gather of y, staged so each lane gets 16 consecutive values
-        if (cnt == WT_TILE) {
+        if (a.ypay) {
+            // streaming path: y travels with the row ids, no gather
+            const double *yp = a.ypay + (int64_t)f * a.col_stride + sg.start + off;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const int e = i * 32 + lane;
+                sy[i * 34 + lane + (lane >> 4)] = e < cnt ? __ldcs(yp + e) : 0.0;
+            }
+        } else if (cnt == WT_TILE) {
+            // coalesced read of the row ids, gather of y, staged so each lane gets 16 consecutive values
             int r[WT_ITEMS];
 #pragma unroll
             for (int i = 0; i < WT_ITEMS; ++i) r[i] = ld_stream_i32(col + i * 32 + lane);
@@ -227,7 +147,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
             out.score2 = best.g2;
             out.k = best.k == 0x7fffffff ? -1 : best.k;
             out.f = f;
-            partials[(int64_t)(sg.pbase + td.tin) * a.F_search + f] = out;
+            partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
         }
     }
 }
@@ -242,12 +162,13 @@ __global__ void __launch_bounds__(256) exact_total_kernel(LevelArgs a, const int
     const int seg = list[gw];
     const SegDev sg = a.segs[seg];
     const int *col = a.orders + (int64_t)total_col * a.col_stride + sg.start;
+    const double *yp = a.ypay ? a.ypay + (int64_t)total_col * a.col_stride + sg.start : nullptr;
     double S = 0.0;
-    double yv = lane < sg.n ? __ldg(a.y + col[lane]) : 0.0;
+    double yv = lane < sg.n ? (yp ? yp[lane] : __ldg(a.y + col[lane])) : 0.0;
     for (int base = 0; base < sg.n; base += 32) {
         const double cur = yv;
         const int nx = base + 32 + lane;
-        yv = nx < sg.n ? __ldg(a.y + col[nx]) : 0.0;
+        yv = nx < sg.n ? (yp ? yp[nx] : __ldg(a.y + col[nx])) : 0.0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) S = __dadd_rn(S, shfl_d(cur, j));
     }
@@ -266,13 +187,14 @@ __global__ void __launch_bounds__(256) l2_exact_kernel(LevelArgs a, const int *_
     const int n = sg.n;
     const double mean = __ddiv_rn(exact_total[seg], (double)n);  // one.py:57  ys[-1][-1] / n
     const int *col = a.orders + (int64_t)f * a.col_stride + sg.start;
+    const double *yp = a.ypay ? a.ypay + (int64_t)f * a.col_stride + sg.start : nullptr;
     double S = 0.0;
     Cand best = cand_none();
-    double yv = lane < n ? __ldg(a.y + col[lane]) : 0.0;
+    double yv = lane < n ? (yp ? yp[lane] : __ldg(a.y + col[lane])) : 0.0;
     for (int base = 0; base < n; base += 32) {
         const double cur = yv;
         const int nx = base + 32 + lane;
-        yv = nx < n ? __ldg(a.y + col[nx]) : 0.0;
+        yv = nx < n ? (yp ? yp[nx] : __ldg(a.y + col[nx])) : 0.0;
         double mine = 0.0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -303,7 +225,7 @@ __global__ void __launch_bounds__(256) l2_exact_kernel(LevelArgs a, const int *_
         out.score2 = best.g2;
         out.k = best.k == 0x7fffffff ? -1 : best.k;
         out.f = f;
-        partials[(int64_t)sg.pbase * a.F_search + f] = out;
+        partials[(int64_t)(sg.pbase + sg.pside) * a.F_search + f] = out;
     }
 }
 
@@ -363,10 +285,11 @@ __global__ void __launch_bounds__(128) finalize_slices_kernel(LevelArgs a, const
     const int seg = blockIdx.y;
     const SegDev sg = a.segs[seg];
     const int64_t count = (int64_t)sg.np * a.F_search;
-    const Partial *p = partials + (int64_t)sg.pbase * a.F_search;
     Partial b = partial_none();
-    for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < count; r += (int64_t)FIN_SLICES * 128)
-        partial_merge(b, p[r]);
+    for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < count; r += (int64_t)FIN_SLICES * 128) {
+        const int64_t j = r / a.F_search, f = r - j * a.F_search;
+        partial_merge(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
+    }
     b = partial_block_reduce(b, sp);
     if (threadIdx.x == 0) sliced[(int64_t)seg * FIN_SLICES + blockIdx.x] = b;
 }
@@ -380,14 +303,16 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
     const int seg = blockIdx.x;
     const SegDev sg = a.segs[seg];
     const int tid = threadIdx.x;
-    int64_t count = (int64_t)sg.np * a.F_search;
-    const Partial *p = partials + (int64_t)sg.pbase * a.F_search;
-    if (sliced) {
-        count = FIN_SLICES;
-        p = sliced + (int64_t)seg * FIN_SLICES;
-    }
     Partial b = partial_none();
-    for (int64_t r = tid; r < count; r += 128) partial_merge(b, p[r]);
+    if (sliced) {
+        for (int r = tid; r < FIN_SLICES; r += 128) partial_merge(b, sliced[(int64_t)seg * FIN_SLICES + r]);
+    } else {
+        const int64_t count = (int64_t)sg.np * a.F_search;
+        for (int64_t r = tid; r < count; r += 128) {
+            const int64_t j = r / a.F_search, f = r - j * a.F_search;
+            partial_merge(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
+        }
+    }
     const Partial w = partial_block_reduce(b, sp);
     if (tid == 0) {
         b200dt_candidate c;

@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // One warp owns one tile of PT_TILE positions of one (node, column).  Every lane sees every
 // ballot, so the running left-count of the tile lives in registers: no shared memory, no
 // block barrier.  Persistent grid, static tile-major order (see l2.cu).
+template <bool PAY>
 __global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
+                                                           const double *__restrict__ y_in, double *__restrict__ y_out,
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
                                                            const u32 *__restrict__ mask, u64 *status, u32 epoch,
@@ -46,12 +48,21 @@ __global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict
         const int cnt = min(PT_TILE, sg.n - off);
         const int *col = in + (int64_t)f * col_stride + sg.start + off;
         int rows[PT_ITEMS];
+        double yv[PAY ? PT_ITEMS : 1];
+        const double *ycol = PAY ? y_in + (int64_t)f * col_stride + sg.start + off : nullptr;
         if (cnt == PT_TILE) {
 #pragma unroll
             for (int i = 0; i < PT_ITEMS; ++i) rows[i] = ld_stream_i32(col + i * 32 + lane);
+            if (PAY) {
+#pragma unroll
+                for (int i = 0; i < PT_ITEMS; ++i) yv[i] = __ldcs(ycol + i * 32 + lane);
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < PT_ITEMS; ++i) rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
+            for (int i = 0; i < PT_ITEMS; ++i) {
+                rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
+                if (PAY) yv[i] = (i * 32 + lane < cnt) ? __ldcs(ycol + i * 32 + lane) : 0.0;
+            }
         }
         u32 leftbits = 0;  // bit i: item i of this lane goes left
 #pragma unroll
@@ -71,6 +82,7 @@ __global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict
         }
         int lb_row = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, run, lane);
         int *ocol = out + (int64_t)f * col_stride + sg.start;
+        double *oy = PAY ? y_out + (int64_t)f * col_stride + sg.start : nullptr;
 #pragma unroll
         for (int i = 0; i < PT_ITEMS; ++i) {
             const int e = i * 32 + lane;
@@ -78,6 +90,7 @@ __global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict
                 const int lb = lb_row + __popc(bal[i] & lt);  // left rows before this element
                 const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
                 ocol[dest] = rows[i];
+                if (PAY) oy[dest] = yv[i];
             }
             lb_row += __popc(bal[i]);
         }
@@ -103,18 +116,24 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
-                     u64 *status, u32 epoch, u32 *ticket) {
+                     u64 *status, u32 epoch, u32 *ticket, const double *y_in, double *y_out) {
     (void)ticket;
     if (n_tiles <= 0) return 0;
+    const bool pay = y_in != nullptr && y_out != nullptr;
     const int64_t total = (int64_t)n_tiles * F_store;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_kernel, 256, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+    const void *kern = pay ? (const void *)partition_kernel<true> : (const void *)partition_kernel<false>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
-    partition_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, col_stride, segs, tiles, n_tiles,
-                                                              mask, status, epoch, F_store);
+    if (pay)
+        partition_kernel<true><<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, y_in, y_out, col_stride,
+                                                                        segs, tiles, n_tiles, mask, status, epoch, F_store);
+    else
+        partition_kernel<false><<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, nullptr, nullptr,
+                                                                         col_stride, segs, tiles, n_tiles, mask, status,
+                                                                         epoch, F_store);
     CK(cudaGetLastError());
     return 0;
 }

@@ -16,6 +16,10 @@ struct HNode {
     int left = -1, right = -1;
     double value = 0.0;
     bool leaf = false;
+    // candidates already produced for this node by the fused level kernel of its parent:
+    // slots fp_base + 2 * tile + fp_side, tile < fp_np
+    bool has_fused = false;
+    int fp_base = 0, fp_np = 0, fp_side = 0;
 };
 
 struct Session {
@@ -27,6 +31,7 @@ struct Session {
     const double *dX = nullptr, *dy = nullptr;
     int64_t ldx = 0;
     int *ord[2] = {nullptr, nullptr};
+    double *ypay[2] = {nullptr, nullptr};  // y travelling with the row ids (L2 fits); null = gather path
     int cur = 0;
     int64_t col_stride = 0;
     std::vector<HNode> nodes;
@@ -42,7 +47,12 @@ struct Session {
     u32 *d_own_mask = nullptr;
     // partition plan produced by decide
     std::vector<SegDev> plan_segs;
+    std::vector<PlanSeg> plan_fused;   // same nodes, for the fused level kernel (payload sessions)
     std::vector<TileDesc> plan_tiles;
+    bool fuse_levels = false;  // B200DT_FUSE=1: partition + search of the children in one kernel (fused.cu)
+    int fused_slots = 0;       // candidate slots of the CURRENT level written by the fused kernel
+    int next_fused_slots = 0;  // ... of the level being planned
+    size_t next_partial_slots = 0;  // candidate slots the next level needs in total
     int64_t plan_elems = 0;
     bool exact_round_done = false;
     // L1 leaves whose median is still to be read from the y-order column: those that live in the

@@ -261,27 +261,37 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
 
 // Sort every column of dX (device, row-major, row stride ldx).  Result: d_out[f*col_stride + j]
 // = row id of the j-th smallest value of column f.  d_alt is scratch of the same shape.
+// ext_keys0/1 (optional): caller-provided key double-buffer of ext_key_capacity uint64 each (the
+// fit lends its y-payload buffers, which are idle during the sort), instead of own scratch.
 int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
-                        int *d_out, int *d_alt, int64_t col_stride) {
+                        int *d_out, int *d_alt, int64_t col_stride, u64 *ext_keys0, u64 *ext_keys1,
+                        int64_t ext_key_capacity) {
     if (N <= 0 || F <= 0) return 0;
     if (N > (int64_t)RS_VAL_MASK) return ctx->fail_msg("argsort: N must be < 2^30");
     cudaStream_t s = ctx->stream;
     const int tiles = (int)((N + RS_TILE - 1) / RS_TILE);
-    // column batch: bound the key double-buffer to a fraction of the free memory
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = free_b / 3;
-    const size_t cap = (size_t)24 << 30;
-    if (budget > cap) budget = cap;
-    int64_t fb_max = (int64_t)(budget / (16ull * (size_t)N));
+    int64_t fb_max;
+    const bool ext = ext_keys0 && ext_keys1 && ext_key_capacity >= (int64_t)PREP_COLS * N;
+    if (ext) {
+        fb_max = ext_key_capacity / N;
+    } else {
+        // column batch: bound the key double-buffer to a fraction of the free memory
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = free_b / 3;
+        const size_t cap = (size_t)24 << 30;
+        if (budget > cap) budget = cap;
+        fb_max = (int64_t)(budget / (16ull * (size_t)N));
+    }
     fb_max = (fb_max / PREP_COLS) * PREP_COLS;
     if (fb_max < PREP_COLS) fb_max = PREP_COLS;
     int64_t Fb = F < fb_max ? ((F + PREP_COLS - 1) / PREP_COLS) * PREP_COLS : fb_max;
-    // reuse what is already allocated if it is big enough for a smaller batch
-    u64 *keys0, *keys1;
+    u64 *keys0 = ext_keys0, *keys1 = ext_keys1;
     u32 *hist, *status;
-    CKR(scratch_get(ctx, SB_KEYS0, (size_t)Fb * N * 8, (void **)&keys0));
-    CKR(scratch_get(ctx, SB_KEYS1, (size_t)Fb * N * 8, (void **)&keys1));
+    if (!ext || Fb * N > ext_key_capacity) {
+        CKR(scratch_get(ctx, SB_KEYS0, (size_t)Fb * N * 8, (void **)&keys0));
+        CKR(scratch_get(ctx, SB_KEYS1, (size_t)Fb * N * 8, (void **)&keys1));
+    }
     CKR(scratch_get(ctx, SB_SORT_HIST, (size_t)Fb * 8 * 256 * 4 * 2, (void **)&hist));
     const size_t status_bytes = (size_t)Fb * tiles * 256 * 4 + 16;
     CKR(scratch_get(ctx, SB_SORT_STATUS, status_bytes, (void **)&status));

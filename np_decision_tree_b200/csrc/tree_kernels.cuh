@@ -19,6 +19,16 @@ struct SegDev {
     int np;         // number of slots (tiles, or 1 for a sequentially scanned node)
     int nleft;      // partition: rows going left
     int exact;      // 1: searched by the sequential-order kernel
+    int pstep;      // candidate slot j of this node is pbase + j * pstep + pside: (1, 0) for slots of
+    int pside;      // its own; (2, side) when the fused level kernel scored it from its parent's tiles
+};
+
+// One split node handed to the fused level kernel (partition + search of the children).
+struct PlanSeg {
+    double total_l, total_r;  // sums of y over the children (their means are total / n)
+    int start, n, nleft;
+    int fbase;                // candidate slot of (tile tin, side) = fbase + 2 * tin + side
+    int score_l, score_r;     // 1: that child is searched by the parallel scan at the next level
 };
 
 struct TileDesc {
@@ -39,7 +49,8 @@ struct LevelArgs {
     const int *orders;      // [F_store][col_stride] row ids, feature-major
     int64_t col_stride;
     int F_search;           // columns searched (local feature slice)
-    const double *y;
+    const double *y;        // (N,) targets by row id (gather path)
+    const double *ypay;     // [F_store][col_stride] y travelling with each row id (streaming path), or null
     const SegDev *segs;
     int n_segs;
 };
@@ -144,7 +155,89 @@ __device__ __forceinline__ int lookback_count(u64 *status, int64_t idx, int tin,
     if (lane == 0) st_relaxed_u64(status + idx, (2ull << 62) | tag | (u32)(excl + tile_count));
     return excl;
 }
+// Look-back of the fused level kernel: (left count, left sum, right sum) in one 48-byte slot of six
+// tagged words: [count | sumL.lo | sumL.hi | sumR.lo | sumR.hi | spare], each [63:34] epoch,
+// [33:32] state, [31:0] payload.  Valid when the five used words agree on (epoch, state).
+struct Carry3 {
+    int c;
+    double l, r;
+};
+
+__device__ __forceinline__ void status3_publish(u64 *slot, u32 epoch, u32 state, int c, double l, double r) {
+    const u64 tag = ((u64)epoch << 34) | ((u64)state << 32);
+    const u64 lb = (u64)__double_as_longlong(l), rb = (u64)__double_as_longlong(r);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(tag | (u64)(u32)c),
+                 "l"(tag | (lb & 0xffffffffull)) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2), "l"(tag | (lb >> 32)),
+                 "l"(tag | (rb & 0xffffffffull)) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 4), "l"(tag | (rb >> 32)), "l"(tag)
+                 : "memory");
+}
+
+__device__ __forceinline__ u32 status3_read(const u64 *slot, u32 epoch, Carry3 &v) {
+    u64 w0, w1, w2, w3, w4, w5;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(slot + 2) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w4), "=l"(w5) : "l"(slot + 4) : "memory");
+    const u32 t0 = (u32)(w0 >> 32);
+    const bool same = t0 == (u32)(w1 >> 32) && t0 == (u32)(w2 >> 32) && t0 == (u32)(w3 >> 32) &&
+                      t0 == (u32)(w4 >> 32);
+    v.c = (int)(u32)w0;
+    v.l = __longlong_as_double((long long)((w1 & 0xffffffffull) | (w2 << 32)));
+    v.r = __longlong_as_double((long long)((w3 & 0xffffffffull) | (w4 << 32)));
+    return (same && (t0 >> 2) == epoch) ? (t0 & 3u) : 0u;
+}
+
+__device__ __forceinline__ Carry3 lookback3(u64 *status, int64_t idx, int tin, u32 epoch, Carry3 tile, int lane) {
+    Carry3 excl{0, 0.0, 0.0};
+    if (tin == 0) {
+        if (lane == 0) status3_publish(status + 6 * idx, epoch, 2u, tile.c, tile.l, tile.r);
+        return excl;
+    }
+    if (lane == 0) status3_publish(status + 6 * idx, epoch, 1u, tile.c, tile.l, tile.r);
+    int remaining = tin;
+    int64_t look = idx - 1;
+    while (true) {
+        const bool in_range = lane < remaining;
+        u32 state;
+        int first;
+        Carry3 val{0, 0.0, 0.0};
+        while (true) {
+            state = 2u;
+            if (in_range) state = status3_read(status + 6 * (look - lane), epoch, val);
+            const u32 ready = __ballot_sync(FULL_MASK, state != 0u);
+            const u32 incl = __ballot_sync(FULL_MASK, state == 2u);
+            first = __ffs(incl) - 1;
+            const u32 need = first < 0 || first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+            if ((ready & need) == need) break;
+        }
+        const bool use = in_range && (first < 0 || lane <= first);
+        int c = use ? val.c : 0;
+        double l = use ? val.l : 0.0, r = use ? val.r : 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            c += __shfl_xor_sync(FULL_MASK, c, m);
+            l += shfl_xor_d(l, m);
+            r += shfl_xor_d(r, m);
+        }
+        excl.c += c;
+        excl.l += l;
+        excl.r += r;
+        if (first >= 0) break;
+        look -= 32;
+        remaining -= 32;
+    }
+    if (lane == 0) status3_publish(status + 6 * idx, epoch, 2u, excl.c + tile.c, excl.l + tile.l, excl.r + tile.r);
+    return excl;
+}
 #endif  // __CUDACC__
+
+int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, int *ord_out, double *y_out,
+                       int64_t col_stride, int F_store, int F_search, const PlanSeg *plan, const TileDesc *tiles,
+                       int n_tiles, int64_t n_elems, const u32 *mask, u64 *status, u32 epoch, Partial *partials,
+                       int variant);
+int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, double *ypay, int64_t col_stride,
+                          int F_store, int64_t N);
 
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles,
                    int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant);
@@ -157,4 +250,4 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
                      int n_marks, int max_left, u32 *mask);
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
-                     u64 *status, u32 epoch, u32 *ticket);
+                     u64 *status, u32 epoch, u32 *ticket, const double *y_in = nullptr, double *y_out = nullptr);
