@@ -56,6 +56,8 @@ struct b200dt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;        // host->device copies that overlap the sort
+    std::vector<cudaEvent_t> copy_events;
     std::string err;
     int sm_count = 148;
 

@@ -173,13 +173,31 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     s->col_stride = (N + 31) / 32 * 32;
 
     // inputs on the device
+    // host inputs: X is copied in column batches on a second stream so that the sort of batch b
+    // overlaps the PCIe transfer of batch b+1 (pinned host memory makes the copies asynchronous)
+    const int64_t h2d_cols = 64;
+    int n_h2d = 0;
     if (space == B200DT_HOST) {
         double *dX, *dy;
         CKR(scratch_get(ctx, SB_X, (size_t)N * F_local * 8, (void **)&dX));
         CKR(scratch_get(ctx, SB_Y, (size_t)N * 8, (void **)&dy));
-        CK(cudaMemcpy2DAsync(dX, (size_t)F_local * 8, X, (size_t)ldx * 8, (size_t)F_local * 8, (size_t)N,
-                             cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        n_h2d = (int)((F_local + h2d_cols - 1) / h2d_cols);
+        while ((int)ctx->copy_events.size() < n_h2d + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->copy_events.push_back(e);
+        }
+        // the copy stream must not overtake earlier work of the main stream on these buffers
+        CK(cudaEventRecord(ctx->copy_events[n_h2d], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[n_h2d], 0));
+        CK(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        for (int b = 0; b < n_h2d; ++b) {
+            const int64_t c0 = b * h2d_cols, fb = std::min<int64_t>(h2d_cols, F_local - c0);
+            CK(cudaMemcpy2DAsync(dX + c0, (size_t)F_local * 8, X + c0, (size_t)ldx * 8, (size_t)fb * 8, (size_t)N,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->copy_events[b], ctx->copy_stream));
+        }
         s->dX = dX;
         s->ldx = F_local;
         s->dy = dy;
@@ -206,7 +224,16 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         k1 = (u64 *)s->ypay[1];
     }
     // one sort per fit (one.py:139)
-    CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
+    if (n_h2d > 0) {
+        for (int b = 0; b < n_h2d; ++b) {
+            const int64_t c0 = b * h2d_cols, fb = std::min<int64_t>(h2d_cols, F_local - c0);
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[b], 0));
+            CKR(sort_columns_device(ctx, s->dX + c0, N, fb, s->ldx, s->ord[0] + c0 * s->col_stride,
+                                    s->ord[1] + c0 * s->col_stride, s->col_stride, k0, k1, kcap));
+        }
+    } else {
+        CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
+    }
     if (!owns_last && last_col) {
         const double *dl = last_col;
         int64_t ld = last_col_ld;
@@ -682,6 +709,8 @@ void b200dt_destroy(b200dt_ctx *ctx) {
     for (auto p : ctx->pinned)
         if (p) cudaFreeHost(p);
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
