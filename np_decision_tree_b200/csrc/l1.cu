@@ -50,23 +50,79 @@ __global__ void __launch_bounds__(256) l1_rank_kernel(const int *__restrict__ yc
     }
 }
 
-// largest set bit strictly below c / smallest set bit strictly above c (they exist by construction)
-__device__ __forceinline__ int bm_prev(const u32 *bm, int c) {
-    int w = c >> 5;
-    u32 m = bm[w] & ((1u << (c & 31)) - 1u);
-    while (m == 0u) m = bm[--w];
-    return (w << 5) + 31 - __clz(m);
-}
-__device__ __forceinline__ int bm_next(const u32 *bm, int c) {
-    int w = c >> 5;
-    u32 m = (c & 31) == 31 ? 0u : (bm[w] & ~((2u << (c & 31)) - 1u));
-    while (m == 0u) m = bm[++w];
-    return (w << 5) + __ffs(m) - 1;
-}
+// Bitmap over ranks with the two words holding the current medians cached in registers: once the
+// set is dense the neighbour search never leaves the cached word, so the per-insertion critical
+// path is register arithmetic; the shared-memory read-modify-write of the insertion is off it.
+struct Walk {
+    u32 *bm;
+    int m, lo, hi;
+    int wlo, whi;     // word indices of lo / hi
+    u32 vlo, vhi;     // cached contents of those words (kept in sync with bm)
+
+    __device__ __forceinline__ void load_lo() { wlo = lo >> 5; vlo = bm[wlo]; }
+    __device__ __forceinline__ void load_hi() { whi = hi >> 5; vhi = bm[whi]; }
+
+    // largest set bit strictly below c (c lives in word wc with cached value vc); it exists
+    __device__ __forceinline__ int prev_of(int c, int wc, u32 vc) const {
+        u32 mk = vc & ((1u << (c & 31)) - 1u);
+        int w = wc;
+        while (mk == 0u) mk = bm[--w];
+        return (w << 5) + 31 - __clz(mk);
+    }
+    // smallest set bit strictly above c
+    __device__ __forceinline__ int next_of(int c, int wc, u32 vc) const {
+        u32 mk = (c & 31) == 31 ? 0u : (vc & ~((2u << (c & 31)) - 1u));
+        int w = wc;
+        while (mk == 0u) mk = bm[++w];
+        return (w << 5) + __ffs(mk) - 1;
+    }
+
+    __device__ __forceinline__ void insert(int r) {
+        const int w = r >> 5;
+        const u32 bit = 1u << (r & 31);
+        bm[w] |= bit;
+        if (m == 0) {
+            lo = hi = r;
+            wlo = whi = w;
+            vlo = vhi = bit;
+        } else {
+            if (w == wlo) vlo |= bit;
+            if (w == whi) vhi |= bit;
+            if (m & 1) {
+                // odd -> even: the single median c stays one of the pair (pyx:23-33)
+                if (r < lo) {
+                    lo = prev_of(hi, whi, vhi);
+                    if ((lo >> 5) != wlo) load_lo();
+                } else {
+                    hi = next_of(lo, wlo, vlo);
+                    if ((hi >> 5) != whi) load_hi();
+                }
+            } else {
+                // even -> odd: the new median is the old lower, the old upper, or r (pyx:34-38)
+                if (r < lo) {
+                    hi = lo;
+                    whi = wlo;
+                    vhi = vlo;
+                } else if (r > hi) {
+                    lo = hi;
+                    wlo = whi;
+                    vlo = vhi;
+                } else {
+                    lo = hi = r;
+                    wlo = whi = w;
+                    vlo = vhi = bm[w];
+                }
+            }
+        }
+        ++m;
+    }
+};
 
 // One warp per (node, column, direction).  dir 0: positions 0..n-1 (prefix medians), dir 1:
 // positions n-1..0 (suffix medians).  out_lo/out_hi[(dir*F+f)*stride + start + pos] = ranks of the
 // (lower, upper) median of the elements scanned up to and including position pos.
+// All 32 lanes run the walk redundantly on identical state (ranks are broadcast by shuffle, lane j
+// keeps the pair of step j), so there is no divergence and no staging through shared memory.
 __global__ void __launch_bounds__(32) l1_median_walk_kernel(const int *__restrict__ orders, int64_t stride, int F,
                                                             const L1Seg *__restrict__ segs,
                                                             const int *__restrict__ lrank, int *__restrict__ out_lo,
@@ -80,53 +136,52 @@ __global__ void __launch_bounds__(32) l1_median_walk_kernel(const int *__restric
     const L1Seg sg = segs[(b >> 1) / F];
     const int n = sg.n;
     const int words = (n + 31) >> 5;
-    int *sin = reinterpret_cast<int *>(smem);
-    int *slo = sin + 32, *shi = sin + 64;
-    u32 *bm = gbitmap ? gbitmap + (int64_t)b * gwords_per_block : smem + 96;
-    for (int w = lane; w < words; w += 32) bm[w] = 0u;
+    Walk wk;
+    wk.bm = gbitmap ? gbitmap + (int64_t)b * gwords_per_block : smem;
+    for (int w = lane; w < words; w += 32) wk.bm[w] = 0u;
     __syncwarp();
+    wk.m = wk.lo = wk.hi = wk.wlo = wk.whi = 0;
+    wk.vlo = wk.vhi = 0u;
     const int *col = orders + (int64_t)f * stride + sg.start;
     int *olo = out_lo + ((int64_t)dir * F + f) * stride + sg.start;
     int *ohi = out_hi + ((int64_t)dir * F + f) * stride + sg.start;
-    int m = 0, lo = 0, hi = 0;
-    for (int q0 = 0; q0 < n; q0 += 32) {
+    // software pipeline: the ranks of the next 32 positions are fetched while this chunk is walked
+    auto fetch = [&](int q0) -> int {
         const int q = q0 + lane;
+        if (q >= n) return 0;
         const int pos = dir ? n - 1 - q : q;
-        if (q < n) sin[lane] = direct_ranks ? col[pos] : lrank[col[pos]];
-        __syncwarp();
-        if (lane == 0) {
-            const int cnt = min(32, n - q0);
-            for (int j = 0; j < cnt; ++j) {
-                const int r = sin[j];
-                bm[r >> 5] |= 1u << (r & 31);
-                if (m == 0) {
-                    lo = hi = r;
-                } else if (m & 1) {
-                    // odd -> even: the single median c stays one of the pair (pyx:23-33)
-                    if (r < lo)
-                        lo = bm_prev(bm, hi);
-                    else
-                        hi = bm_next(bm, lo);
-                } else {
-                    // even -> odd: the new median is the old lower, the old upper, or r (pyx:34-38)
-                    if (r < lo)
-                        hi = lo;
-                    else if (r > hi)
-                        lo = hi;
-                    else
-                        lo = hi = r;
+        return direct_ranks ? col[pos] : lrank[col[pos]];
+    };
+    int nxt = fetch(0);
+    for (int q0 = 0; q0 < n; q0 += 32) {
+        const int mine = nxt;
+        nxt = fetch(q0 + 32);
+        int mylo = 0, myhi = 0;
+        if (q0 + 32 <= n) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                wk.insert(__shfl_sync(FULL_MASK, mine, j));
+                if (lane == j) {
+                    mylo = wk.lo;
+                    myhi = wk.hi;
                 }
-                ++m;
-                slo[j] = lo;
-                shi[j] = hi;
+            }
+        } else {
+            const int cnt = n - q0;
+            for (int j = 0; j < cnt; ++j) {
+                wk.insert(__shfl_sync(FULL_MASK, mine, j));
+                if (lane == j) {
+                    mylo = wk.lo;
+                    myhi = wk.hi;
+                }
             }
         }
-        __syncwarp();
+        const int q = q0 + lane;
         if (q < n) {
-            olo[pos] = slo[lane];
-            ohi[pos] = shi[lane];
+            const int pos = dir ? n - 1 - q : q;
+            olo[pos] = mylo;
+            ohi[pos] = myhi;
         }
-        __syncwarp();
     }
 }
 
@@ -279,14 +334,14 @@ const int WALK_SMEM_MAX = 220 * 1024;
 int launch_walk(b200dt_ctx *ctx, const int *orders, int64_t stride, int F, const L1Seg *d_segs, int n_segs,
                 int max_n, int64_t n_elems, const int *lrank, int *med_lo, int *med_hi, int direct_ranks) {
     const size_t words = (size_t)(max_n + 31) / 32;
-    const size_t smem = 96 * 4 + words * 4;
+    const size_t smem = words * 4 + 16;
     const int blocks = n_segs * F * 2;
     u32 *gbm = nullptr;
     size_t use_smem = smem;
     if (smem > (size_t)WALK_SMEM_MAX) {
         // rank bitmap too large for shared memory (> ~1.8 M rows in one node): keep it in HBM/L2
         CKR(scratch_get(ctx, SB_L1_H, (size_t)blocks * words * 4, (void **)&gbm));
-        use_smem = 96 * 4;
+        use_smem = 16;
     }
     static bool attr_done = false;
     if (!attr_done) {

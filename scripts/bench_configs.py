@@ -1,0 +1,112 @@
+"""Side measurements of the other BASELINE.json configs (bench.py carries only the headline, C4).
+
+    python scripts/bench_configs.py [c2] [c3] [c5] [--cpu]
+
+C2: make_regression 10 000 x 100, L2 depth 10 fit + inference (README.md:60-64: 390 ms reference)
+C3: L1 build_regression_tree_v2 depth 1, 1 M x 100 (cummedian path; BASELINE.md: 138 s on one core)
+C5: inference of a depth-10 tree, N x 256 device-resident rows on one GPU (row-sharded across GPUs
+    with no exchange, so N per GPU is what matters; default 12.5 M = the 8-GPU share of 100 M)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from np_decision_tree_b200 import _lib  # noqa: E402
+from np_decision_tree_b200.decision_tree import one, strategy_l1, utils  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c3", "c5"]
+with_cpu = "--cpu" in sys.argv
+out = {}
+
+
+def best_of(fn, n=5):
+    ts = []
+    for _ in range(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), r
+
+
+if "c2" in args:
+    from sklearn.datasets import make_regression
+    X, y = make_regression(n_samples=10000, n_features=100, random_state=0)
+    one.build_regression_tree(X, y, max_depth=10)
+    t_fit, tree = best_of(lambda: one.build_regression_tree(X, y, max_depth=10))
+    t_inf, p = best_of(lambda: utils.inference(X, tree))
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    t_fit_d, _ = best_of(lambda: one.build_regression_tree(Xd, yd, max_depth=10))
+    out["c2"] = {"fit_ms_numpy_in": t_fit * 1e3, "fit_ms_device_in": t_fit_d * 1e3, "inference_ms_numpy_in": t_inf * 1e3,
+                 "nodes": tree.max_node_ + 1, "train_mse": float(np.mean((p - y) ** 2)),
+                 "rows_features_per_s": 1e6 / t_fit_d}
+    if with_cpu:
+        import oracle
+        t0 = time.perf_counter()
+        o = oracle.fit_l2(X, y, max_depth=10)
+        out["c2"]["cpu_port_fit_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        oracle.predict(X, o)
+        out["c2"]["cpu_port_inference_ms"] = (time.perf_counter() - t0) * 1e3
+
+if "c3" in args:
+    rs = np.random.RandomState(0)
+    N, F = 1_000_000, 100
+    X = rs.standard_normal((N, F))
+    coef = np.zeros(F)
+    coef[rs.permutation(F)[:10]] = 100 * rs.uniform(size=10)
+    y = X @ coef
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    strategy_l1.build_regression_tree_v2(Xd, yd, max_depth=1)
+    ctx = _lib.default_context(0)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    t_fit, tree = best_of(lambda: strategy_l1.build_regression_tree_v2(Xd, yd, max_depth=1), n=3)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    out["c3"] = {"fit_ms_device_in": t_fit * 1e3, "rows_features_per_s": N * F / t_fit,
+                 "root_feature": int(tree.tree_.feature[0]), "root_threshold": float(tree.tree_.threshold[0]),
+                 "kernels_ms_per_fit": {k: v["ms"] / 3 for k, v in prof.items()}}
+    del Xd, yd
+
+if "c5" in args:
+    N = int(os.environ.get("C5_ROWS", 12_500_000))
+    F = 256
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    # a depth-10 tree fitted on a 1 M-row sample of the same distribution
+    Xs = torch.randn((1_000_000, F), dtype=torch.float64, device="cuda", generator=g)
+    cols = torch.arange(0, 250, 25, device="cuda")
+    ys = (Xs[:, cols] * torch.linspace(10, 100, 10, dtype=torch.float64, device="cuda")).sum(1)
+    tree = one.build_regression_tree(Xs, ys, max_depth=10)
+    del Xs, ys
+    X = torch.randn((N, F), dtype=torch.float64, device="cuda", generator=g)
+    utils.inference(X, tree)
+    ctx = _lib.default_context(0)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    t_inf, p = best_of(lambda: utils.inference(X, tree), n=5)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    k = prof["predict"]
+    leaf = utils.inference_leaf(X[:100000], tree)
+    out["c5"] = {"rows": N, "features": F, "nodes": tree.max_node_ + 1, "predict_ms": t_inf * 1e3,
+                 "kernel_ms": k["ms"] / k["launches"], "rows_per_s": N / t_inf, "rows_features_per_s": N * F / t_inf,
+                 "alg_bytes_per_row": k["alg_bytes"] / k["launches"] / N,
+                 "alg_gbs": k["alg_bytes"] / k["ms"] / 1e6, "full_row_stream_gbs": N * F * 8 / (k["ms"] / k["launches"]) / 1e6}
+    if with_cpu:
+        import oracle
+        Xc = X[:2_000_000].cpu().numpy()
+        t0 = time.perf_counter()
+        oracle.predict(Xc, tree)
+        dt = time.perf_counter() - t0
+        out["c5"]["cpu_port_rows_per_s_on_2M_rows"] = 2_000_000 / dt
+
+print(json.dumps(out, indent=1))
