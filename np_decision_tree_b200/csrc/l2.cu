@@ -21,9 +21,11 @@
 namespace {
 
 
+template <int VARIANT>
 __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
                                                          int n_tiles, ScanStatus st, u32 epoch,
-                                                         Partial *__restrict__ partials, int variant) {
+                                                         Partial *__restrict__ partials) {
+    constexpr int variant = VARIANT;
     __shared__ double sy_all[8][SY_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *sy = sy_all[warp];
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
 
         // score of every position of this lane; best and runner-up tracked branch-free
         const int n = sg.n;
-        const double mean = sg.total / (double)n;
+        const double mean = sg.total * rcp_fast1((double)n);   // approximate search: 1e-12 is plenty
         const int k0 = off + lane * WT_ITEMS;
         double m1 = -CUDART_INF, m2 = -CUDART_INF, sbest = 0.0, dbest = 0.0;
         int ibest = -1;
@@ -350,9 +352,13 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
     if (n_tiles <= 0) return 0;
     const int64_t total = (int64_t)n_tiles * a.F_search;
     // every block must be resident at once (tiles wait on earlier tiles): grid <= occupancy limit
-    const int grid = persistent_grid(ctx, (const void *)l2_scan_kernel, 256, (total + 7) / 8);
+    const void *kern = variant == 1 ? (const void *)l2_scan_kernel<1> : (const void *)l2_scan_kernel<2>;
+    const int grid = persistent_grid(ctx, kern, 256, (total + 7) / 8);
     LaunchScope ls(ctx, KC_L2_SCAN, 12.0 * (double)n_elems * a.F_search);
-    l2_scan_kernel<<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials, variant);
+    if (variant == 1)
+        l2_scan_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
+    else
+        l2_scan_kernel<2><<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
     CK(cudaGetLastError());
     return 0;
 }

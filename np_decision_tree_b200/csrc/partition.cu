@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // ballot, so the running left-count of the tile lives in registers: no shared memory, no
 // block barrier.  Persistent grid, static tile-major order (see l2.cu).
 template <bool PAY>
-__global__ void __launch_bounds__(256, 3) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
+__global__ void __launch_bounds__(256, PAY ? 2 : 3) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                            const double *__restrict__ y_in, double *__restrict__ y_out,
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
