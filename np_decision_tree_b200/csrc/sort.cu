@@ -19,7 +19,10 @@ namespace {
 #define RS_THREADS_DEF 256
 #endif
 constexpr int RS_THREADS = RS_THREADS_DEF;
-constexpr int RS_ITEMS = 4096 / RS_THREADS;
+#ifndef RS_ITEMS_DEF
+#define RS_ITEMS_DEF 16
+#endif
+constexpr int RS_ITEMS = RS_ITEMS_DEF;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_AGG = 1u << 30;
@@ -117,7 +120,7 @@ struct RsSmem {
 };
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
+__global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 16 ? 2 : 3) radix_pass_kernel(
     const u64 *__restrict__ keys_in, const int *__restrict__ vals_in, u64 *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
     int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {

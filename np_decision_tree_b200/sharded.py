@@ -52,7 +52,7 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
                 min_improvement=1e-7, min_sample_leaf=1, v=1, group=None, ctx=None):
     """Grow one tree over columns sharded across the ranks of ``group``.
 
-    X_local: (N, F_local) float64 torch CUDA tensor -- this rank's columns
+    X_local: (N, F_local) float64 torch tensor, CUDA or (pinned) host -- this rank's columns
              [col_offset, col_offset + F_local) of the global (N, n_features) matrix.
     y:       (N,) float64 CUDA tensor, replicated.
     last_col: (N,) float64 CUDA tensor = global column n_features-1, required on ranks that do
@@ -63,9 +63,15 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    if not (X_local.is_cuda and y.is_cuda):
-        raise TypeError("fit_sharded takes CUDA tensors")
-    dev = X_local.device
+    if X_local.is_cuda != y.is_cuda:
+        raise TypeError("X_local and y must both be CUDA tensors or both be host tensors")
+    on_device = X_local.is_cuda
+    if on_device:
+        dev = X_local.device
+    else:
+        # host (ideally pinned) tensors: the library copies the column batches on a second stream
+        # while it sorts the ones already there
+        dev = torch.device("cuda", torch.cuda.current_device())
     ctx = ctx or _lib.default_context(dev.index)
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     X_local = X_local.contiguous()
@@ -73,10 +79,13 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
     N, F_local = X_local.shape
     lc_ptr, lc_ld = None, 0
     if last_col is not None and col_offset + F_local != n_features:
+        if last_col.is_cuda != on_device:
+            raise TypeError("last_col must live where X_local lives")
         lc_ptr, lc_ld = last_col.data_ptr(), last_col.stride(0)
+    space = _lib.DEVICE if on_device else _lib.HOST
     lib, h = ctx.lib, ctx.handle
     ctx.check(lib.b200dt_session_begin(h, X_local.data_ptr(), y.data_ptr(), N, F_local, X_local.stride(0),
-                                       _lib.DEVICE, criterion, int(max_depth), float(min_improvement),
+                                       space, criterion, int(max_depth), float(min_improvement),
                                        int(min_sample_leaf), 1 if v == 1 else 2, int(col_offset),
                                        int(n_features), lc_ptr, lc_ld))
     mask = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
