@@ -287,9 +287,10 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     // them every live node reserves slots of its own (its tiles when it must be scanned here -- the
     // root, or any node of a gather-path session -- else one, for the sequential search)
     int pbase = s->fused_slots;
+    const int scan_tile = l2_scan_tile(s->ypay[0] != nullptr);
     for (int i = 0; i < n_live; ++i) {
         const HNode &nd = s->nodes[s->live[i]];
-        const int ntiles = (nd.n + WT_TILE - 1) / WT_TILE;
+        const int ntiles = (nd.n + scan_tile - 1) / scan_tile;
         SegDev sg;
         sg.total = nd.total;
         sg.start = nd.start;
@@ -537,7 +538,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     size_t slots = (size_t)s->next_fused_slots + 1;
     for (int c : next_live) {
         const HNode &ch = s->nodes[c];
-        slots += ch.has_fused ? 1 : (size_t)(ch.n + WT_TILE - 1) / WT_TILE;
+        slots += ch.has_fused ? 1 : (size_t)(ch.n + WT_TILE - 1) / WT_TILE;   // upper bound for either tile size
     }
     s->next_partial_slots = slots;
     s->fused_slots = s->next_fused_slots;

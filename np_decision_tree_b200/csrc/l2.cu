@@ -16,6 +16,8 @@
 //    adds y in sorted order ONE ELEMENT AT A TIME in fp64 (shuffle broadcast), with the
 //    reference's exact operation order and no FMA contraction, so bit-exact gain ties
 //    between features resolve exactly as in the reference (hard part 1).
+#include <algorithm>
+
 #include "l2_score.cuh"
 
 namespace {
@@ -140,6 +142,117 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
         best.s = sbest;
         best.dev = dbest;
         best.k = ibest < 0 ? 0x7fffffff : k0 + ibest;
+        cand_warp_reduce(best);
+        if (lane == 0) {
+            Partial out;
+            out.score = best.g;
+            out.aux = best.dev;
+            out.lsum = best.s;
+            out.score2 = best.g2;
+            out.k = best.k == 0x7fffffff ? -1 : best.k;
+            out.f = f;
+            partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
+        }
+    }
+}
+
+// Streaming variant (sessions that carry y as a payload next to the row ids): the tile is 1024
+// positions of ypay, staged once in shared memory and read twice by the lane that owns 32
+// consecutive positions -- first to sum them (tile aggregate -> look-back), then to rebuild the
+// running prefix while scoring.  No per-lane prefix array, rolled loops, and the per-tile costs
+// (look-back, warp arg-max, segment decode) are amortised over twice as many elements.
+constexpr int ST_PITCH = ST_TILE + ST_TILE / 32;  // 1 pad double per 32: conflict-free blocked reads
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
+                                                                int n_tiles, ScanStatus st, u32 epoch,
+                                                                Partial *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sy = reinterpret_cast<double *>(scan_smem) + warp * ST_PITCH;
+    const double *mine = sy + lane * (ST_ITEMS + 1);   // position lane*32 + j sits at lane*33 + j
+    const int64_t total_tiles = (int64_t)n_tiles * a.F_search;
+    const int64_t stride_tiles = (int64_t)gridDim.x * 8;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += stride_tiles) {
+        const int f = (int)(t % a.F_search), ti = (int)(t / a.F_search);
+        const TileDesc td = tiles[ti];
+        const SegDev sg = a.segs[td.seg];
+        const int off = td.tin * ST_TILE;
+        const int cnt = min(ST_TILE, sg.n - off);
+        const double *yp = a.ypay + (int64_t)f * a.col_stride + sg.start + off;
+        if (cnt == ST_TILE) {
+#pragma unroll
+            for (int i = 0; i < ST_ITEMS; ++i) sy[i * 33 + lane] = __ldcs(yp + i * 32 + lane);
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < ST_ITEMS; ++i) {
+                const int e = i * 32 + lane;
+                sy[i * 33 + lane] = e < cnt ? __ldcs(yp + e) : 0.0;
+            }
+        }
+        __syncwarp();
+        double tsum = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < ST_ITEMS; ++j) tsum += mine[j];
+        double incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = shfl_up_d(incl, d);
+            if (lane >= d) incl += o;
+        }
+        const double tile_total = shfl_d(incl, 31);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        double S = excl + (incl - tsum);   // sum of everything before this lane's first position
+
+        const int n = sg.n;
+        const double mean = sg.total * rcp_fast1((double)n);
+        const int k0 = off + lane * ST_ITEMS;
+        // positions this lane may score: inside the tile and not the node's last row
+        const int nvalid = max(0, min(ST_ITEMS, min(cnt - lane * ST_ITEMS, n - 1 - k0)));
+        double m1 = -CUDART_INF, m2 = -CUDART_INF, sbest = 0.0, dbest = 0.0;
+        int kbest = 0x7fffffff;
+        if (VARIANT == 1 && n <= (1 << 24)) {
+            double km = (double)(k0 + 1) * mean;
+            double den = (double)(k0 + 1) * (double)(n - 1 - k0);
+            double dd = (double)(n - 2 * k0 - 3);
+#pragma unroll 4
+            for (int j = 0; j < nvalid; ++j) {
+                S += mine[j];
+                const double dev = S - km;
+                const double g = dev * dev * rcp_fast1(den);
+                m2 = fmax(m2, fmin(m1, g));
+                if (g > m1) {
+                    m1 = g;
+                    sbest = S;
+                    dbest = dev;
+                    kbest = k0 + j;
+                }
+                km += mean;
+                den += dd;
+                dd -= 2.0;
+            }
+            dbest = fabs(dbest);
+        } else {
+            for (int j = 0; j < nvalid; ++j) {
+                S += mine[j];
+                double dev = 0.0;
+                const double g = score_fast(S, k0 + j, n, mean, VARIANT, dev);
+                m2 = fmax(m2, fmin(m1, g));
+                if (g > m1) {
+                    m1 = g;
+                    sbest = S;
+                    dbest = dev;
+                    kbest = k0 + j;
+                }
+            }
+        }
+        __syncwarp();  // sy is overwritten by the next tile
+        Cand best;
+        best.g = m1;
+        best.g2 = m2;
+        best.s = sbest;
+        best.dev = dbest;
+        best.k = kbest;
         cand_warp_reduce(best);
         if (lane == 0) {
             Partial out;
@@ -351,10 +464,30 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
     (void)ticket;
     if (n_tiles <= 0) return 0;
     const int64_t total = (int64_t)n_tiles * a.F_search;
+    LaunchScope ls(ctx, KC_L2_SCAN, 12.0 * (double)n_elems * a.F_search);
+    if (a.ypay) {
+        // streaming kernel: tiles of ST_TILE positions (the host builds the tile list accordingly)
+        const size_t smem = 8 * ST_PITCH * sizeof(double);
+        static bool attr_done = false;
+        if (!attr_done) {
+            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        const void *kern = variant == 1 ? (const void *)l2_scan_stream_kernel<1> : (const void *)l2_scan_stream_kernel<2>;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        int64_t grid = std::min<int64_t>((int64_t)per_sm * ctx->sm_count, (total + 7) / 8);
+        if (variant == 1)
+            l2_scan_stream_kernel<1><<<(unsigned)grid, 256, smem, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
+        else
+            l2_scan_stream_kernel<2><<<(unsigned)grid, 256, smem, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
+        CK(cudaGetLastError());
+        return 0;
+    }
     // every block must be resident at once (tiles wait on earlier tiles): grid <= occupancy limit
     const void *kern = variant == 1 ? (const void *)l2_scan_kernel<1> : (const void *)l2_scan_kernel<2>;
     const int grid = persistent_grid(ctx, kern, 256, (total + 7) / 8);
-    LaunchScope ls(ctx, KC_L2_SCAN, 12.0 * (double)n_elems * a.F_search);
     if (variant == 1)
         l2_scan_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
     else

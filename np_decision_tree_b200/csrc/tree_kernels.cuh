@@ -7,6 +7,8 @@ constexpr int WT_ITEMS = 16;
 constexpr int WT_TILE = 32 * WT_ITEMS;   // K2: 512 sorted positions per warp tile
 constexpr int PT_ITEMS = 16;
 constexpr int PT_TILE = 32 * PT_ITEMS;   // K4: 512 sorted positions per warp tile
+constexpr int ST_ITEMS = 32;
+constexpr int ST_TILE = 32 * ST_ITEMS;   // K2 streaming (y payload): 1024 positions per warp tile
 constexpr int EXACT_ROWS = 2048;         // nodes up to this size take the sequential-order search
 
 // One node of the current level = one contiguous segment [start, start+n) of every column of
@@ -241,6 +243,8 @@ int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, d
 
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles,
                    int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant);
+// tile size the search of this session uses (the streaming kernel takes larger tiles)
+static inline int l2_scan_tile(bool payload) { return payload ? ST_TILE : WT_TILE; }
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small,
                     int64_t n_elems, int total_col, double *exact_total, Partial *partials, int variant);
 constexpr int FIN_SLICES_HOST = 64;  // == FIN_SLICES in l2.cu

@@ -87,7 +87,8 @@ with open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w") as f:
         wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
         traffic[name].append(rd + wr)
 cls = {"radix_pass_kernel<0, 0>": "sort_radix_pass", "l2_scan_kernel": "l2_scan_search",
-       "partition_kernel": "partition", "sort_prepare_kernel": "sort_prepare"}
+       "partition_kernel": "partition", "sort_prepare_kernel": "sort_prepare",
+       "gather_payload_kernel": "gather_y_payload"}
 tj = {}
 for name, vals in traffic.items():
     for k, c in cls.items():
