@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // ballot, so the running left-count of the tile lives in registers: no shared memory, no
 // block barrier.  Persistent grid, static tile-major order (see l2.cu).
 template <bool PAY>
-__global__ void __launch_bounds__(256, PAY ? 2 : 3) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
+__global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                            const double *__restrict__ y_in, double *__restrict__ y_out,
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
@@ -46,23 +46,15 @@ __global__ void __launch_bounds__(256, PAY ? 2 : 3) partition_kernel(const int *
         const SegDev sg = segs[td.seg];
         const int off = td.tin * PT_TILE;
         const int cnt = min(PT_TILE, sg.n - off);
-        const int *col = in + (int64_t)f * col_stride + sg.start + off;
+        const int64_t cbase = (int64_t)f * col_stride + sg.start;
+        const int *col = in + cbase + off;
         int rows[PT_ITEMS];
-        double yv[PAY ? PT_ITEMS : 1];
-        const double *ycol = PAY ? y_in + (int64_t)f * col_stride + sg.start + off : nullptr;
         if (cnt == PT_TILE) {
 #pragma unroll
             for (int i = 0; i < PT_ITEMS; ++i) rows[i] = ld_stream_i32(col + i * 32 + lane);
-            if (PAY) {
-#pragma unroll
-                for (int i = 0; i < PT_ITEMS; ++i) yv[i] = __ldcs(ycol + i * 32 + lane);
-            }
         } else {
 #pragma unroll
-            for (int i = 0; i < PT_ITEMS; ++i) {
-                rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
-                if (PAY) yv[i] = (i * 32 + lane < cnt) ? __ldcs(ycol + i * 32 + lane) : 0.0;
-            }
+            for (int i = 0; i < PT_ITEMS; ++i) rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
         }
         u32 leftbits = 0;  // bit i: item i of this lane goes left
 #pragma unroll
@@ -71,28 +63,38 @@ __global__ void __launch_bounds__(256, PAY ? 2 : 3) partition_kernel(const int *
             const bool is_left = row >= 0 && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
             leftbits |= (is_left ? 1u : 0u) << i;
         }
-        // ballots of the item rows; every lane sees all of them, so the tile's left count and the
-        // left rows before each item row are register arithmetic (same value in every lane)
+        // every lane sees every ballot, so the tile's left count is register arithmetic; the ballots
+        // are recomputed in the write loop instead of being kept (registers -> occupancy)
         int run = 0;
-        u32 bal[PT_ITEMS];
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) {
-            bal[i] = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
-            run += __popc(bal[i]);
-        }
+        for (int i = 0; i < PT_ITEMS; ++i) run += __popc(__ballot_sync(FULL_MASK, (leftbits >> i) & 1u));
         int lb_row = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, run, lane);
-        int *ocol = out + (int64_t)f * col_stride + sg.start;
-        double *oy = PAY ? y_out + (int64_t)f * col_stride + sg.start : nullptr;
+        int *ocol = out + cbase;
+        const double *ycol = PAY ? y_in + cbase + off : nullptr;
+        double *oy = PAY ? y_out + cbase : nullptr;
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) {
-            const int e = i * 32 + lane;
-            if (e < cnt) {
-                const int lb = lb_row + __popc(bal[i] & lt);  // left rows before this element
-                const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
-                ocol[dest] = rows[i];
-                if (PAY) oy[dest] = yv[i];
+        for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
+            double yv[4];
+            if (PAY) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = (i0 + u) * 32 + lane;
+                    yv[u] = e < cnt ? __ldcs(ycol + e) : 0.0;
+                }
             }
-            lb_row += __popc(bal[i]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                const u32 b = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
+                const int e = i * 32 + lane;
+                if (e < cnt) {
+                    const int lb = lb_row + __popc(b & lt);  // left rows before this element
+                    const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
+                    ocol[dest] = rows[i];
+                    if (PAY) oy[dest] = yv[u];
+                }
+                lb_row += __popc(b);
+            }
         }
     }
 }
