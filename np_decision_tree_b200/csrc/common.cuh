@@ -205,6 +205,14 @@ static inline void prof_drain(b200dt_ctx *ctx) {
     ctx->prof_pending.clear();
 }
 
+// Persistent kernels whose tiles wait on lower-numbered tiles need every block resident at once.
+// A cooperative launch makes the runtime REFUSE a grid that cannot be co-resident (e.g. SMs taken by
+// another client) instead of letting it dead-lock on the device.
+static inline cudaError_t launch_resident(const void *kernel, unsigned grid, unsigned block, void **args,
+                                          size_t smem, cudaStream_t stream) {
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(block), args, smem, stream);
+}
+
 // ---------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------

@@ -231,14 +231,9 @@ int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, i
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_LEVEL_FUSED, 21.0 * (double)n_elems * F_store);
-    if (variant == 1)
-        level_fused_kernel<1><<<(unsigned)grid, 256, smem, ctx->stream>>>(ord_in, y_in, ord_out, y_out, col_stride, F_store,
-                                                                       F_search, plan, tiles, n_tiles, mask, status,
-                                                                       epoch, partials);
-    else
-        level_fused_kernel<2><<<(unsigned)grid, 256, smem, ctx->stream>>>(ord_in, y_in, ord_out, y_out, col_stride, F_store,
-                                                                       F_search, plan, tiles, n_tiles, mask, status,
-                                                                       epoch, partials);
+    void *args[] = {&ord_in, &y_in, &ord_out, &y_out, &col_stride, &F_store, &F_search, &plan, &tiles, &n_tiles,
+                    &mask, &status, &epoch, &partials};
+    CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));
     CK(cudaGetLastError());
     return 0;
 }

@@ -478,21 +478,17 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         int64_t grid = std::min<int64_t>((int64_t)per_sm * ctx->sm_count, (total + 7) / 8);
-        if (variant == 1)
-            l2_scan_stream_kernel<1><<<(unsigned)grid, 256, smem, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
-        else
-            l2_scan_stream_kernel<2><<<(unsigned)grid, 256, smem, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
-        CK(cudaGetLastError());
+        LevelArgs a_ = a;
+        void *args[] = {&a_, &tiles, &n_tiles, &st, &epoch, &partials};
+        CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));
         return 0;
     }
     // every block must be resident at once (tiles wait on earlier tiles): grid <= occupancy limit
     const void *kern = variant == 1 ? (const void *)l2_scan_kernel<1> : (const void *)l2_scan_kernel<2>;
     const int grid = persistent_grid(ctx, kern, 256, (total + 7) / 8);
-    if (variant == 1)
-        l2_scan_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
-    else
-        l2_scan_kernel<2><<<grid, 256, 0, ctx->stream>>>(a, tiles, n_tiles, st, epoch, partials);
-    CK(cudaGetLastError());
+    LevelArgs a_ = a;
+    void *args[] = {&a_, &tiles, &n_tiles, &st, &epoch, &partials};
+    CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
     return 0;
 }
 

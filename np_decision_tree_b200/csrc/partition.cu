@@ -129,13 +129,11 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
-    if (pay)
-        partition_kernel<true><<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, y_in, y_out, col_stride,
-                                                                        segs, tiles, n_tiles, mask, status, epoch, F_store);
-    else
-        partition_kernel<false><<<(unsigned)grid, 256, 0, ctx->stream>>>(orders_in, orders_out, nullptr, nullptr,
-                                                                         col_stride, segs, tiles, n_tiles, mask, status,
-                                                                         epoch, F_store);
+    const double *yi = pay ? y_in : nullptr;
+    double *yo = pay ? y_out : nullptr;
+    void *args[] = {&orders_in, &orders_out, &yi, &yo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status, &epoch,
+                    &F_store};
+    CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
     CK(cudaGetLastError());
     return 0;
 }
