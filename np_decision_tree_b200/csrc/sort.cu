@@ -2,27 +2,34 @@
 //
 // replaces np.argsort(X, axis=0)   (ref decision_tree/one.py:139, strategy_l1.py:147,177)
 //
-// Stable LSD radix sort, 8 passes of 8-bit digits over the order-preserving uint64 image of
-// each key, payload = int32 row id, every column of a batch in the same launch.
+// Stable LSD radix sort on the order-preserving uint64 image of each key, payload = int32 row id,
+// every column of a batch in the same launch.  Two paths, same result:
+//
+//  * 64-bit path (always correct): 8 onesweep passes of 8-bit digits over the full key.
+//      prepare 16 B + passes 20 + 6*24 + 16 = 196 algorithmic bytes per element.
+//  * 32-bit path (default, falls back per column): the radix passes are bound by their scattered
+//    DRAM traffic (ncu: 56 % of peak bytes/s; cutting instructions changed nothing), so the lever
+//    is fewer bytes.  Sort only the TOP 32 bits of the key (4 passes of 4-byte keys: 12+16+16+12 B),
+//    then one fix-up pass gathers the full key of every element (one 32-byte sector) and stably
+//    sorts the short runs that tie on the top 32 bits.  prepare 12 + passes 56 + fix-up 44 = 112
+//    bytes per element.  A run longer than FIX_MAX_RUN (heavy duplicates, integer-valued or
+//    constant columns) flags its column, which is then re-sorted by the 64-bit path.
+//
 //   prepare : X[n][f] (coalesced 64-byte row pieces) -> keys[f][n] through a shared-memory
-//             transpose, plus all 8 digit histograms per column (shared-memory atomics)
+//             transpose, plus the digit histograms of every pass (shared-memory atomics)
 //   pass p  : "onesweep": one read of (key, row id), one scattered write.  A tile's global
 //             digit offsets come from a decoupled look-back over the tiles before it in the
-//             same column; tiles are handed out by an atomic ticket so every predecessor of
-//             a running tile has started.
-// Algorithmic bytes per element: prepare 16; pass 0: 20; passes 1..6: 24; pass 7: 16 => 196.
+//             same column; tiles are handed out by an atomic ticket in tile-major order.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
 
-#ifndef RS_THREADS_DEF
-#define RS_THREADS_DEF 256
-#endif
-constexpr int RS_THREADS = RS_THREADS_DEF;
-#ifndef RS_ITEMS_DEF
-#define RS_ITEMS_DEF 16
-#endif
-constexpr int RS_ITEMS = RS_ITEMS_DEF;
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_AGG = 1u << 30;
@@ -32,6 +39,9 @@ constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
 constexpr int PREP_COLS = 8;     // columns per prepare block: 64-byte row pieces
 constexpr int PREP_ROWS = 256;   // rows per chunk
 constexpr int PREP_PITCH = PREP_ROWS + 1;
+
+constexpr int FIX_TILE = 1024;   // fix-up: positions per block
+constexpr int FIX_MAX_RUN = 32;  // longest run (equal top-32 bits) repaired in place
 
 // float64 -> uint64 whose unsigned order equals the float order.
 // NaN sorts last (like numpy); -0.0 is folded onto +0.0 so the sort equals a stable argsort.
@@ -43,16 +53,26 @@ __device__ __forceinline__ u64 sortable_key(double x) {
     return b ^ flip;
 }
 
+template <typename KeyT>
+__device__ __forceinline__ KeyT narrow_key(u64 k);
+template <>
+__device__ __forceinline__ u64 narrow_key<u64>(u64 k) { return k; }
+template <>
+__device__ __forceinline__ u32 narrow_key<u32>(u64 k) { return (u32)(k >> 32); }
+
+// histograms: ghist[col][8][256] (only the first sizeof(KeyT) digit slots are used)
+template <typename KeyT>
 __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restrict__ X, int64_t N,
-                                                           int64_t ldx, int fb, u64 *__restrict__ keys,
+                                                           int64_t ldx, int fb, KeyT *__restrict__ keys,
                                                            int64_t kstride, u32 *__restrict__ ghist) {
+    constexpr int NPASS = (int)sizeof(KeyT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u32 *hist = reinterpret_cast<u32 *>(smem_raw);                              // [8 cols][8 digits][256]
-    u64 *tile = reinterpret_cast<u64 *>(smem_raw + PREP_COLS * 8 * 256 * 4);    // [8][PREP_PITCH]
+    u32 *hist = reinterpret_cast<u32 *>(smem_raw);                                  // [8 cols][NPASS][256]
+    KeyT *tile = reinterpret_cast<KeyT *>(smem_raw + PREP_COLS * NPASS * 256 * 4);  // [8][PREP_PITCH]
     const int tid = threadIdx.x;
     const int cg = blockIdx.y;
     const int ncols = min(PREP_COLS, fb - cg * PREP_COLS);
-    for (int i = tid; i < PREP_COLS * 8 * 256; i += 256) hist[i] = 0;
+    for (int i = tid; i < PREP_COLS * NPASS * 256; i += 256) hist[i] = 0;
     __syncthreads();
     const int tcol = tid & (PREP_COLS - 1);
     const int trow = tid >> 3;  // 32 rows per sweep
@@ -70,11 +90,11 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
             const int rr = it * 32 + trow;
             const int64_t r = r0 + rr;
             if (r < N && tcol < ncols) {
-                const u64 k = sortable_key(xv[it]);
+                const KeyT k = narrow_key<KeyT>(sortable_key(xv[it]));
                 tile[tcol * PREP_PITCH + rr] = k;
-                u32 *h = hist + tcol * 8 * 256;
+                u32 *h = hist + tcol * NPASS * 256;
 #pragma unroll
-                for (int d = 0; d < 8; ++d) atomicAdd(&h[d * 256 + (u32)((k >> (8 * d)) & 255)], 1u);
+                for (int d = 0; d < NPASS; ++d) atomicAdd(&h[d * 256 + (u32)((k >> (8 * d)) & 255)], 1u);
             }
         }
         __syncthreads();
@@ -84,9 +104,10 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
         }
         __syncthreads();
     }
-    for (int i = tid; i < ncols * 8 * 256; i += 256) {
+    for (int i = tid; i < ncols * NPASS * 256; i += 256) {
         const u32 c = hist[i];
-        if (c) atomicAdd(&ghist[(int64_t)cg * PREP_COLS * 8 * 256 + i], c);
+        const int col = i / (NPASS * 256), rest = i % (NPASS * 256);
+        if (c) atomicAdd(&ghist[((int64_t)cg * PREP_COLS + col) * 8 * 256 + rest], c);
     }
 }
 
@@ -109,23 +130,31 @@ __global__ void __launch_bounds__(256) sort_scan_hist_kernel(const u32 *__restri
     gbase[(int64_t)blockIdx.x * 256 + tid] = base + incl - c;
 }
 
+template <typename KeyT>
 struct RsSmem {
     u32 warp_hist[RS_WARPS][256];
     u32 gofs[256];
     u32 warp_sums[8];
     u32 ticket;
     u32 pad[3];
-    u64 keys[RS_TILE];
+    KeyT keys[RS_TILE];
     int vals[RS_TILE];
 };
 
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 16 ? 2 : 3) radix_pass_kernel(
-    const u64 *__restrict__ keys_in, const int *__restrict__ vals_in, u64 *__restrict__ keys_out,
+template <typename KeyT>
+__device__ __forceinline__ KeyT ld_stream_key(const KeyT *p);
+template <>
+__device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stream_u64(p); }
+template <>
+__device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return (u32)ld_stream_i32((const int *)p); }
+
+template <typename KeyT, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
+    const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in, KeyT *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
     int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
+    RsSmem<KeyT> &sm = *reinterpret_cast<RsSmem<KeyT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sm.ticket = atomicAdd(ticket_ctr, 1u);
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
@@ -139,22 +168,22 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 16 ? 2 : 3) radix_pass_
     const bool full = count == RS_TILE;
     const int shift = pass * 8;
     // everything below indexes with 32-bit tile-local offsets from these bases
-    const u64 *kin = keys_in + (int64_t)col * kstride + base;
+    const KeyT *kin = keys_in + (int64_t)col * kstride + base;
     const int *vin = FIRST ? nullptr : vals_in + (int64_t)col * vstride + base;
     const int o0 = warp * (32 * RS_ITEMS) + lane;  // this lane's item 0; item i is o0 + 32 i
 
-    u64 key[RS_ITEMS];
+    KeyT key[RS_ITEMS];
     int val[RS_ITEMS];
     if (full) {
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) key[i] = ld_stream_u64(kin + o0 + i * 32);
+        for (int i = 0; i < RS_ITEMS; ++i) key[i] = ld_stream_key<KeyT>(kin + o0 + i * 32);
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) val[i] = FIRST ? (int)base + o0 + i * 32 : ld_stream_i32(vin + o0 + i * 32);
     } else {
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const bool v = o0 + i * 32 < count;
-            key[i] = v ? ld_stream_u64(kin + o0 + i * 32) : ~0ull;
+            key[i] = v ? ld_stream_key<KeyT>(kin + o0 + i * 32) : (KeyT)~(KeyT)0;
             val[i] = FIRST ? (int)base + o0 + i * 32 : (v ? ld_stream_i32(vin + o0 + i * 32) : 0);
         }
     }
@@ -246,18 +275,140 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 16 ? 2 : 3) radix_pass_
         }
     }
     __syncthreads();
-    u64 *kout = LAST ? nullptr : keys_out + (int64_t)col * kstride;
+    KeyT *kout = LAST ? nullptr : keys_out + (int64_t)col * kstride;
     int *vout = vals_out + (int64_t)col * vstride;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         const int pos = j * RS_THREADS + tid;
         if (full || pos < count) {
-            const u64 k = sm.keys[pos];
+            const KeyT k = sm.keys[pos];
             const u32 dest = sm.gofs[(u32)(k >> shift) & 255u] + (u32)pos;
             if (!LAST) kout[dest] = k;
             vout[dest] = sm.vals[pos];
         }
     }
+}
+
+// Fix-up of the 32-bit path.  in[f][j] is sorted (stably) by the top 32 bits of the key.  A block
+// takes FIX_TILE positions plus a halo, gathers every element's full key, and the thread at the
+// start of each run of equal top-32 bits insertion-sorts that run (stable) by the full key.  A
+// position is written by the tile that owns the START of its run; runs longer than FIX_MAX_RUN
+// flag the column (its output is then discarded).
+__global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restrict__ X, int64_t ldx, int64_t N,
+                                                         const int *__restrict__ in, int *__restrict__ out,
+                                                         int64_t col_stride, int *__restrict__ col_flags) {
+    __shared__ u64 skey[FIX_TILE + FIX_MAX_RUN + 1];
+    __shared__ int srow[FIX_TILE + FIX_MAX_RUN + 1];
+    const int f = blockIdx.y;
+    const int64_t a = (int64_t)blockIdx.x * FIX_TILE;   // first position this tile owns
+    const int *col = in + (int64_t)f * col_stride;
+    int *ocol = out + (int64_t)f * col_stride;
+    // slot s <-> position a - 1 + s  (slot 0 = left neighbour, only used to recognise a run that
+    // started in an earlier tile)
+    const int nslots = (int)min((int64_t)(FIX_TILE + FIX_MAX_RUN + 1), N - a + 1);
+    const int first = a == 0 ? 1 : 0;   // lowest slot holding a real element
+    for (int s = first + threadIdx.x; s < nslots; s += 256) {
+        const int row = col[a - 1 + s];
+        srow[s] = row;
+        skey[s] = sortable_key(__ldg(X + (int64_t)row * ldx + f));
+    }
+    __syncthreads();
+    const int owned = (int)min((int64_t)FIX_TILE, N - a);
+#define HI(s) ((u32)(skey[s] >> 32))
+    for (int s = 1 + threadIdx.x; s <= owned; s += 256) {
+        const u32 hi = HI(s);
+        if (s > first && HI(s - 1) == hi) continue;   // not the start of a run
+        int len = 1;
+        while (s + len < nslots && len <= FIX_MAX_RUN && HI(s + len) == hi) ++len;
+        if (len > FIX_MAX_RUN) {
+            col_flags[f] = 1;   // too long to repair here: this column takes the 64-bit path
+            continue;
+        }
+        // stable insertion sort of slots [s, s+len) by the full key (equal keys are already in row
+        // order, the radix passes being stable)
+        for (int p = 1; p < len; ++p) {
+            const u64 k = skey[s + p];
+            const int r = srow[s + p];
+            int q = p;
+            while (q > 0 && skey[s + q - 1] > k) {
+                skey[s + q] = skey[s + q - 1];
+                srow[s + q] = srow[s + q - 1];
+                --q;
+            }
+            skey[s + q] = k;
+            srow[s + q] = r;
+        }
+    }
+    __syncthreads();
+    for (int s = 1 + threadIdx.x; s < nslots; s += 256) {
+        const u32 hi = HI(s);
+        int b = s, steps = 0;
+        while (b > first && HI(b - 1) == hi && steps <= FIX_MAX_RUN) {
+            --b;
+            ++steps;
+        }
+        // b == 0: the run began in an earlier tile; b > owned: it begins in the next one
+        if (steps <= FIX_MAX_RUN && b >= 1 && b <= owned) ocol[a - 1 + s] = srow[s];
+    }
+#undef HI
+}
+
+template <typename KeyT>
+int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t ldx, KeyT *keys0, KeyT *keys1,
+                   int *v0, int *v1, int64_t col_stride, u32 *ghist, u32 *gbase, u32 *status, int tiles) {
+    // the passes alternate v0, v1, ...; the last one writes v1
+    constexpr int NPASS = (int)sizeof(KeyT);
+    cudaStream_t s = ctx->stream;
+    const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
+    const size_t prep_smem = PREP_COLS * NPASS * 256 * 4 + PREP_COLS * PREP_PITCH * sizeof(KeyT);
+    const size_t pass_smem = sizeof(RsSmem<KeyT>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(sort_prepare_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+        attr_done = true;
+    }
+    CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
+    {
+        int64_t chunks = (N + PREP_ROWS - 1) / PREP_ROWS;
+        int64_t rb = (3ll * ctx->sm_count * 2 + groups - 1) / groups;
+        if (rb > chunks) rb = chunks;
+        if (rb < 1) rb = 1;
+        LaunchScope ls(ctx, KC_SORT_PREPARE, (8.0 + sizeof(KeyT)) * (double)N * fb);
+        sort_prepare_kernel<KeyT><<<dim3((unsigned)rb, groups), 256, prep_smem, s>>>(dX, N, ldx, fb, keys0, N, ghist);
+    }
+    {
+        LaunchScope ls(ctx, KC_MISC, 0.0);
+        sort_scan_hist_kernel<<<fb * 8, 256, 0, s>>>(ghist, gbase);
+    }
+    CK(cudaGetLastError());
+    int *v[2] = {v0, v1};
+    KeyT *k[2] = {keys0, keys1};
+    u32 *ticket = status + (size_t)fb * tiles * 256;
+    for (int p = 0; p < NPASS; ++p) {
+        CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4 + 16, s));
+        const unsigned grid = (unsigned)((int64_t)fb * tiles);
+        const KeyT *kin = k[p & 1];
+        KeyT *kout = k[(p + 1) & 1];
+        const int *vin = v[(p + 1) & 1];
+        int *vout = v[p & 1];
+        const double K = (double)sizeof(KeyT);
+        const double bytes = (p == 0 ? 2 * K + 4 : p == NPASS - 1 ? K + 8 : 2 * K + 8) * (double)N * fb;
+        LaunchScope ls(ctx, KC_SORT_PASS, bytes);
+        if (p == 0)
+            radix_pass_kernel<KeyT, true, false><<<grid, RS_THREADS, pass_smem, s>>>(
+                kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+        else if (p == NPASS - 1)
+            radix_pass_kernel<KeyT, false, true><<<grid, RS_THREADS, pass_smem, s>>>(
+                kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+        else
+            radix_pass_kernel<KeyT, false, false><<<grid, RS_THREADS, pass_smem, s>>>(
+                kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+    }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
@@ -271,7 +422,6 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
                         int64_t ext_key_capacity) {
     if (N <= 0 || F <= 0) return 0;
     if (N > (int64_t)RS_VAL_MASK) return ctx->fail_msg("argsort: N must be < 2^30");
-    cudaStream_t s = ctx->stream;
     const int tiles = (int)((N + RS_TILE - 1) / RS_TILE);
     int64_t fb_max;
     const bool ext = ext_keys0 && ext_keys1 && ext_key_capacity >= (int64_t)PREP_COLS * N;
@@ -295,61 +445,53 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
         CKR(scratch_get(ctx, SB_KEYS0, (size_t)Fb * N * 8, (void **)&keys0));
         CKR(scratch_get(ctx, SB_KEYS1, (size_t)Fb * N * 8, (void **)&keys1));
     }
-    CKR(scratch_get(ctx, SB_SORT_HIST, (size_t)Fb * 8 * 256 * 4 * 2, (void **)&hist));
-    const size_t status_bytes = (size_t)Fb * tiles * 256 * 4 + 16;
+    CKR(scratch_get(ctx, SB_SORT_HIST, (size_t)Fb * 8 * 256 * 4 * 2 + (size_t)F * 4 + 64, (void **)&hist));
+    const size_t status_bytes = (size_t)Fb * tiles * 256 * 4 + 64;
     CKR(scratch_get(ctx, SB_SORT_STATUS, status_bytes, (void **)&status));
     u32 *ghist = hist, *gbase = hist + (size_t)Fb * 8 * 256;
+    int *flags = (int *)(gbase + (size_t)Fb * 8 * 256);
 
-    const size_t prep_smem = PREP_COLS * 8 * 256 * 4 + PREP_COLS * PREP_PITCH * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CK(cudaFuncSetAttribute(sort_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_done = true;
+    static int use32 = -1;
+    if (use32 < 0) {
+        const char *e = getenv("B200DT_SORT64");
+        use32 = (e && e[0] == '1') ? 0 : 1;
     }
+    if (use32) {
+        // ---- 32-bit path: top-32-bit radix sort into d_alt, fix-up into d_out --------------------
+        CK(cudaMemsetAsync(flags, 0, (size_t)F * 4, ctx->stream));
+        for (int64_t c0 = 0; c0 < F; c0 += Fb) {
+            const int fb = (int)(F - c0 < Fb ? F - c0 : Fb);
+            CKR(run_radix_sort<u32>(ctx, dX + c0, N, fb, ldx, (u32 *)keys0, (u32 *)keys1, d_out + c0 * col_stride,
+                                    d_alt + c0 * col_stride, col_stride, ghist, gbase, status, tiles));
+            LaunchScope ls(ctx, KC_SORT_FIXUP, 44.0 * (double)N * fb);
+            sort_fixup_kernel<<<dim3((unsigned)((N + FIX_TILE - 1) / FIX_TILE), (unsigned)fb), 256, 0, ctx->stream>>>(
+                dX + c0, ldx, N, d_alt + c0 * col_stride, d_out + c0 * col_stride, col_stride, flags + c0);
+        }
+        CK(cudaGetLastError());
+        // columns with a long run of equal top-32 bits take the 64-bit path
+        int *h_flags;
+        CKR(pinned_get(ctx, 5, (size_t)F * 4, (void **)&h_flags));
+        CK(cudaMemcpyAsync(h_flags, flags, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int> redo;
+        for (int64_t f = 0; f < F; ++f)
+            if (h_flags[f]) redo.push_back((int)f);
+        size_t i = 0;
+        while (i < redo.size()) {  // contiguous ranges of flagged columns are re-sorted together
+            size_t j = i;
+            while (j + 1 < redo.size() && redo[j + 1] == redo[j] + 1 && (int64_t)(j + 1 - i) < Fb) ++j;
+            const int c0 = redo[i], fb = (int)(j - i + 1);
+            CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + (int64_t)c0 * col_stride,
+                                    d_out + (int64_t)c0 * col_stride, col_stride, ghist, gbase, status, tiles));
+            i = j + 1;
+        }
+        return 0;
+    }
+    // ---- 64-bit path -----------------------------------------------------------------------------
     for (int64_t c0 = 0; c0 < F; c0 += Fb) {
         const int fb = (int)(F - c0 < Fb ? F - c0 : Fb);
-        const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
-        CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
-        {
-            int64_t chunks = (N + PREP_ROWS - 1) / PREP_ROWS;
-            int64_t rb = (3ll * ctx->sm_count * 2 + groups - 1) / groups;
-            if (rb > chunks) rb = chunks;
-            if (rb < 1) rb = 1;
-            LaunchScope ls(ctx, KC_SORT_PREPARE, 16.0 * (double)N * fb);
-            sort_prepare_kernel<<<dim3((unsigned)rb, groups), 256, prep_smem, s>>>(dX + c0, N, ldx, fb, keys0, N, ghist);
-        }
-        {
-            LaunchScope ls(ctx, KC_MISC, 0.0);
-            sort_scan_hist_kernel<<<fb * 8, 256, 0, s>>>(ghist, gbase);
-        }
-        CK(cudaGetLastError());
-        int *v[2] = {d_alt + c0 * col_stride, d_out + c0 * col_stride};
-        u64 *k[2] = {keys0, keys1};
-        u32 *ticket = status + (size_t)Fb * tiles * 256;
-        for (int p = 0; p < 8; ++p) {
-            CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4, s));
-            CK(cudaMemsetAsync(ticket, 0, 16, s));
-            const unsigned grid = (unsigned)((int64_t)fb * tiles);
-            const u64 *kin = k[p & 1];
-            u64 *kout = k[(p + 1) & 1];
-            const int *vin = v[(p + 1) & 1];
-            int *vout = v[p & 1];
-            const double bytes = (p == 0 ? 20.0 : p == 7 ? 16.0 : 24.0) * (double)N * fb;
-            LaunchScope ls(ctx, KC_SORT_PASS, bytes);
-            if (p == 0)
-                radix_pass_kernel<true, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-            else if (p == 7)
-                radix_pass_kernel<false, true><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-            else
-                radix_pass_kernel<false, false><<<grid, RS_THREADS, sizeof(RsSmem), s>>>(
-                    kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-        }
-        CK(cudaGetLastError());
+        CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + c0 * col_stride,
+                                d_out + c0 * col_stride, col_stride, ghist, gbase, status, tiles));
     }
     return 0;
 }
