@@ -9,11 +9,12 @@
 //      prepare 16 B + passes 20 + 6*24 + 16 = 196 algorithmic bytes per element.
 //  * 32-bit path (default, falls back per column): the radix passes are bound by their scattered
 //    DRAM traffic (ncu: 56 % of peak bytes/s; cutting instructions changed nothing), so the lever
-//    is fewer bytes.  Sort only the TOP 32 bits of the key (4 passes of 4-byte keys: 12+16+16+12 B),
-//    then one fix-up pass gathers the full key of every element (one 32-byte sector) and stably
-//    sorts the short runs that tie on the top 32 bits.  prepare 12 + passes 56 + fix-up 44 = 112
-//    bytes per element.  A run longer than FIX_MAX_RUN (heavy duplicates, integer-valued or
-//    constant columns) flags its column, which is then re-sorted by the 64-bit path.
+//    is fewer bytes.  Sort a 32-bit order-preserving IMAGE of the key (linear quantisation of the
+//    value between the column's min and max; 4 passes of 4-byte keys), then one fix-up pass streams
+//    the sorted images, gathers the full key only of elements whose image is shared (~1 % for smooth
+//    data) and stably sorts those short runs.  min/max 8 + prepare 12 + passes 12+16+16+16 + fix-up
+//    12 = 92 bytes per element.  A run longer than FIX_MAX_RUN (heavy duplicates, integer-valued,
+//    constant or outlier-dominated columns) flags its column, which the 64-bit path re-sorts.
 //
 //   prepare : X[n][f] (coalesced 64-byte row pieces) -> keys[f][n] through a shared-memory
 //             transpose, plus the digit histograms of every pass (shared-memory atomics)
@@ -23,6 +24,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
+
+#include <math_constants.h>
 
 #include "common.cuh"
 
@@ -53,6 +56,80 @@ __device__ __forceinline__ u64 sortable_key(double x) {
     return b ^ flip;
 }
 
+// 32-bit image of a key for the fast path: LINEAR quantisation of the value between the column's
+// finite minimum and maximum.  x -> (x - mn) * scale is monotone non-decreasing in fp64, so the
+// image is order-preserving (ties only merge neighbours); unlike the top 32 bits of the fp64 bit
+// pattern (20 mantissa bits per binade) it spreads a smooth distribution over all 2^32 slots, so
+// for 10 M standard-normal values ~1 % of the elements share a slot instead of ~70 %.
+struct ColRange {
+    double mn;      // smallest finite value of the column
+    double scale;   // (2^32 - 2) / (max - min), or 0 when the column is constant / not finite
+};
+
+__device__ __forceinline__ u32 quantise(double x, const ColRange r) {
+    if (x != x) return 0xffffffffu;                       // NaN last, like the full key
+    double q = (x - r.mn) * r.scale;                      // -inf -> -inf, +inf -> +inf (scale > 0)
+    if (!(q > 0.0)) q = 0.0;                              // also catches 0 * inf = NaN when scale == 0
+    if (q > 4294967294.0) q = 4294967294.0;
+    return (u32)__double2ull_rz(q);
+}
+
+// per column: min / max over the finite values, as order-preserving u64 keys (atomicMin/Max)
+__global__ void __launch_bounds__(256) col_minmax_kernel(const double *__restrict__ X, int64_t N, int64_t ldx,
+                                                         int fb, u64 *__restrict__ kmin, u64 *__restrict__ kmax) {
+    __shared__ u64 smin[256], smax[256];
+    const int tid = threadIdx.x;
+    const int cg = blockIdx.y;
+    const int ncols = min(PREP_COLS, fb - cg * PREP_COLS);
+    const int tcol = tid & (PREP_COLS - 1), trow = tid >> 3;
+    u64 lo = ~0ull, hi = 0ull;
+    for (int64_t r = (int64_t)blockIdx.x * 32 + trow; r < N; r += (int64_t)gridDim.x * 32) {
+        if (tcol < ncols) {
+            const double x = X[r * ldx + cg * PREP_COLS + tcol];
+            if (x == x && fabs(x) != CUDART_INF) {
+                const u64 k = sortable_key(x);
+                lo = k < lo ? k : lo;
+                hi = k > hi ? k : hi;
+            }
+        }
+    }
+    smin[tid] = lo;
+    smax[tid] = hi;
+    __syncthreads();
+    for (int s = 128; s >= PREP_COLS; s >>= 1) {   // threads with equal (tid & 7) hold the same column
+        if (tid < s) {
+            smin[tid] = smin[tid + s] < smin[tid] ? smin[tid + s] : smin[tid];
+            smax[tid] = smax[tid + s] > smax[tid] ? smax[tid + s] : smax[tid];
+        }
+        __syncthreads();
+    }
+    if (tid < ncols) {
+        atomicMin((unsigned long long *)&kmin[cg * PREP_COLS + tid], (unsigned long long)smin[tid]);
+        atomicMax((unsigned long long *)&kmax[cg * PREP_COLS + tid], (unsigned long long)smax[tid]);
+    }
+}
+
+__device__ __forceinline__ double key_to_double(u64 k) {
+    const u64 b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void col_range_kernel(const u64 *__restrict__ kmin, const u64 *__restrict__ kmax, int fb,
+                                 ColRange *__restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= fb) return;
+    ColRange r;
+    r.mn = 0.0;
+    r.scale = 0.0;
+    if (kmin[f] <= kmax[f]) {
+        const double mn = key_to_double(kmin[f]), mx = key_to_double(kmax[f]);
+        const double span = mx - mn;
+        r.mn = mn;
+        if (span > 0.0 && span < CUDART_INF) r.scale = 4294967294.0 / span;
+    }
+    out[f] = r;
+}
+
 template <typename KeyT>
 __device__ __forceinline__ KeyT narrow_key(u64 k);
 template <>
@@ -64,7 +141,8 @@ __device__ __forceinline__ u32 narrow_key<u32>(u64 k) { return (u32)(k >> 32); }
 template <typename KeyT>
 __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restrict__ X, int64_t N,
                                                            int64_t ldx, int fb, KeyT *__restrict__ keys,
-                                                           int64_t kstride, u32 *__restrict__ ghist) {
+                                                           int64_t kstride, u32 *__restrict__ ghist,
+                                                           const ColRange *__restrict__ ranges) {
     constexpr int NPASS = (int)sizeof(KeyT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32 *hist = reinterpret_cast<u32 *>(smem_raw);                                  // [8 cols][NPASS][256]
@@ -76,6 +154,10 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
     __syncthreads();
     const int tcol = tid & (PREP_COLS - 1);
     const int trow = tid >> 3;  // 32 rows per sweep
+    ColRange rng;
+    rng.mn = 0.0;
+    rng.scale = 0.0;
+    if (sizeof(KeyT) == 4 && tcol < ncols) rng = ranges[cg * PREP_COLS + tcol];
     for (int64_t chunk = blockIdx.x; chunk * PREP_ROWS < N; chunk += gridDim.x) {
         const int64_t r0 = chunk * PREP_ROWS;
         // all 8 loads of this thread first (the smem atomics below would otherwise serialise them)
@@ -90,7 +172,7 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
             const int rr = it * 32 + trow;
             const int64_t r = r0 + rr;
             if (r < N && tcol < ncols) {
-                const KeyT k = narrow_key<KeyT>(sortable_key(xv[it]));
+                const KeyT k = sizeof(KeyT) == 4 ? (KeyT)quantise(xv[it], rng) : narrow_key<KeyT>(sortable_key(xv[it]));
                 tile[tcol * PREP_PITCH + rr] = k;
                 u32 *h = hist + tcol * NPASS * 256;
 #pragma unroll
@@ -289,37 +371,45 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
     }
 }
 
-// Fix-up of the 32-bit path.  in[f][j] is sorted (stably) by the top 32 bits of the key.  A block
-// takes FIX_TILE positions plus a halo, gathers every element's full key, and the thread at the
-// start of each run of equal top-32 bits insertion-sorts that run (stable) by the full key.  A
-// position is written by the tile that owns the START of its run; runs longer than FIX_MAX_RUN
-// flag the column (its output is then discarded).
+// Fix-up of the 32-bit path.  in[f][j] is sorted (stably) by the 32-bit image q[f][j].  A block
+// takes FIX_TILE positions plus a halo; elements whose image is shared with a neighbour gather
+// their full key (one 32-byte sector; ~1 % of the elements for smooth data), and the thread at the
+// start of each run insertion-sorts it (stable) by the full key.  A position is written by the tile
+// that owns the START of its run; runs longer than FIX_MAX_RUN flag the column (its output is then
+// discarded and the column re-sorted by the 64-bit path).
 __global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restrict__ X, int64_t ldx, int64_t N,
+                                                         const u32 *__restrict__ q, int64_t qstride,
                                                          const int *__restrict__ in, int *__restrict__ out,
                                                          int64_t col_stride, int *__restrict__ col_flags) {
     __shared__ u64 skey[FIX_TILE + FIX_MAX_RUN + 1];
+    __shared__ u32 sq[FIX_TILE + FIX_MAX_RUN + 2];
     __shared__ int srow[FIX_TILE + FIX_MAX_RUN + 1];
     const int f = blockIdx.y;
     const int64_t a = (int64_t)blockIdx.x * FIX_TILE;   // first position this tile owns
     const int *col = in + (int64_t)f * col_stride;
+    const u32 *qc = q + (int64_t)f * qstride;
     int *ocol = out + (int64_t)f * col_stride;
     // slot s <-> position a - 1 + s  (slot 0 = left neighbour, only used to recognise a run that
     // started in an earlier tile)
     const int nslots = (int)min((int64_t)(FIX_TILE + FIX_MAX_RUN + 1), N - a + 1);
     const int first = a == 0 ? 1 : 0;   // lowest slot holding a real element
     for (int s = first + threadIdx.x; s < nslots; s += 256) {
-        const int row = col[a - 1 + s];
-        srow[s] = row;
-        skey[s] = sortable_key(__ldg(X + (int64_t)row * ldx + f));
+        srow[s] = col[a - 1 + s];
+        sq[s] = qc[a - 1 + s];
+    }
+    __syncthreads();
+    for (int s = first + threadIdx.x; s < nslots; s += 256) {
+        const bool tied = (s > first && sq[s - 1] == sq[s]) || (s + 1 < nslots && sq[s + 1] == sq[s]);
+        skey[s] = tied ? sortable_key(__ldg(X + (int64_t)srow[s] * ldx + f)) : 0ull;
     }
     __syncthreads();
     const int owned = (int)min((int64_t)FIX_TILE, N - a);
-#define HI(s) ((u32)(skey[s] >> 32))
     for (int s = 1 + threadIdx.x; s <= owned; s += 256) {
-        const u32 hi = HI(s);
-        if (s > first && HI(s - 1) == hi) continue;   // not the start of a run
+        const u32 v = sq[s];
+        if (s > first && sq[s - 1] == v) continue;   // not the start of a run
         int len = 1;
-        while (s + len < nslots && len <= FIX_MAX_RUN && HI(s + len) == hi) ++len;
+        while (s + len < nslots && len <= FIX_MAX_RUN && sq[s + len] == v) ++len;
+        if (len == 1) continue;
         if (len > FIX_MAX_RUN) {
             col_flags[f] = 1;   // too long to repair here: this column takes the 64-bit path
             continue;
@@ -329,34 +419,35 @@ __global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restric
         for (int p = 1; p < len; ++p) {
             const u64 k = skey[s + p];
             const int r = srow[s + p];
-            int q = p;
-            while (q > 0 && skey[s + q - 1] > k) {
-                skey[s + q] = skey[s + q - 1];
-                srow[s + q] = srow[s + q - 1];
-                --q;
+            int t = p;
+            while (t > 0 && skey[s + t - 1] > k) {
+                skey[s + t] = skey[s + t - 1];
+                srow[s + t] = srow[s + t - 1];
+                --t;
             }
-            skey[s + q] = k;
-            srow[s + q] = r;
+            skey[s + t] = k;
+            srow[s + t] = r;
         }
     }
     __syncthreads();
     for (int s = 1 + threadIdx.x; s < nslots; s += 256) {
-        const u32 hi = HI(s);
+        const u32 v = sq[s];
         int b = s, steps = 0;
-        while (b > first && HI(b - 1) == hi && steps <= FIX_MAX_RUN) {
+        while (b > first && sq[b - 1] == v && steps <= FIX_MAX_RUN) {
             --b;
             ++steps;
         }
         // b == 0: the run began in an earlier tile; b > owned: it begins in the next one
         if (steps <= FIX_MAX_RUN && b >= 1 && b <= owned) ocol[a - 1 + s] = srow[s];
     }
-#undef HI
 }
 
 template <typename KeyT>
 int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t ldx, KeyT *keys0, KeyT *keys1,
-                   int *v0, int *v1, int64_t col_stride, u32 *ghist, u32 *gbase, u32 *status, int tiles) {
-    // the passes alternate v0, v1, ...; the last one writes v1
+                   int *v0, int *v1, int64_t col_stride, u32 *ghist, u32 *gbase, u32 *status, int tiles,
+                   const ColRange *ranges, bool keep_keys) {
+    // the passes alternate v0, v1, ...; the last one writes v1 (and, with keep_keys, the sorted
+    // keys into keys0)
     constexpr int NPASS = (int)sizeof(KeyT);
     cudaStream_t s = ctx->stream;
     const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
@@ -377,7 +468,7 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
         if (rb > chunks) rb = chunks;
         if (rb < 1) rb = 1;
         LaunchScope ls(ctx, KC_SORT_PREPARE, (8.0 + sizeof(KeyT)) * (double)N * fb);
-        sort_prepare_kernel<KeyT><<<dim3((unsigned)rb, groups), 256, prep_smem, s>>>(dX, N, ldx, fb, keys0, N, ghist);
+        sort_prepare_kernel<KeyT><<<dim3((unsigned)rb, groups), 256, prep_smem, s>>>(dX, N, ldx, fb, keys0, N, ghist, ranges);
     }
     {
         LaunchScope ls(ctx, KC_MISC, 0.0);
@@ -395,12 +486,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
         const int *vin = v[(p + 1) & 1];
         int *vout = v[p & 1];
         const double K = (double)sizeof(KeyT);
-        const double bytes = (p == 0 ? 2 * K + 4 : p == NPASS - 1 ? K + 8 : 2 * K + 8) * (double)N * fb;
+        const bool last_plain = p == NPASS - 1 && !keep_keys;
+        const double bytes = (p == 0 ? 2 * K + 4 : last_plain ? K + 8 : 2 * K + 8) * (double)N * fb;
         LaunchScope ls(ctx, KC_SORT_PASS, bytes);
         if (p == 0)
             radix_pass_kernel<KeyT, true, false><<<grid, RS_THREADS, pass_smem, s>>>(
                 kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-        else if (p == NPASS - 1)
+        else if (last_plain)
             radix_pass_kernel<KeyT, false, true><<<grid, RS_THREADS, pass_smem, s>>>(
                 kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
         else
@@ -457,18 +549,34 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
         use32 = (e && e[0] == '1') ? 0 : 1;
     }
     if (use32) {
-        // ---- 32-bit path: top-32-bit radix sort into d_alt, fix-up into d_out --------------------
+        // ---- 32-bit path: radix sort of the 32-bit images into d_alt, fix-up into d_out ------------
         CK(cudaMemsetAsync(flags, 0, (size_t)F * 4, ctx->stream));
+        u64 *kmin, *kmax;
+        ColRange *ranges;
+        CKR(scratch_get(ctx, SB_SORT_RANGE, (size_t)Fb * (8 + 8 + sizeof(ColRange)) + 64, (void **)&kmin));
+        kmax = kmin + Fb;
+        ranges = (ColRange *)(kmax + Fb);
         for (int64_t c0 = 0; c0 < F; c0 += Fb) {
             const int fb = (int)(F - c0 < Fb ? F - c0 : Fb);
+            const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
+            CK(cudaMemsetAsync(kmin, 0xff, (size_t)Fb * 8, ctx->stream));
+            CK(cudaMemsetAsync(kmax, 0x00, (size_t)Fb * 8, ctx->stream));
+            {
+                int64_t rb = std::min<int64_t>((N + 31) / 32, std::max<int64_t>(1, 6ll * ctx->sm_count / groups));
+                LaunchScope ls(ctx, KC_SORT_PREPARE, 8.0 * (double)N * fb, 2);
+                col_minmax_kernel<<<dim3((unsigned)rb, groups), 256, 0, ctx->stream>>>(dX + c0, N, ldx, fb, kmin, kmax);
+                col_range_kernel<<<(fb + 127) / 128, 128, 0, ctx->stream>>>(kmin, kmax, fb, ranges);
+            }
+            // 4 passes: keys0 -> keys1 -> keys0 -> keys1 -> keys0 (sorted images), rows end in d_alt
             CKR(run_radix_sort<u32>(ctx, dX + c0, N, fb, ldx, (u32 *)keys0, (u32 *)keys1, d_out + c0 * col_stride,
-                                    d_alt + c0 * col_stride, col_stride, ghist, gbase, status, tiles));
-            LaunchScope ls(ctx, KC_SORT_FIXUP, 44.0 * (double)N * fb);
+                                    d_alt + c0 * col_stride, col_stride, ghist, gbase, status, tiles, ranges, true));
+            LaunchScope ls(ctx, KC_SORT_FIXUP, 12.0 * (double)N * fb);
             sort_fixup_kernel<<<dim3((unsigned)((N + FIX_TILE - 1) / FIX_TILE), (unsigned)fb), 256, 0, ctx->stream>>>(
-                dX + c0, ldx, N, d_alt + c0 * col_stride, d_out + c0 * col_stride, col_stride, flags + c0);
+                dX + c0, ldx, N, (const u32 *)keys0, N, d_alt + c0 * col_stride, d_out + c0 * col_stride, col_stride,
+                flags + c0);
         }
         CK(cudaGetLastError());
-        // columns with a long run of equal top-32 bits take the 64-bit path
+        // columns with a long run of equal 32-bit images take the 64-bit path
         int *h_flags;
         CKR(pinned_get(ctx, 5, (size_t)F * 4, (void **)&h_flags));
         CK(cudaMemcpyAsync(h_flags, flags, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -482,7 +590,8 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
             while (j + 1 < redo.size() && redo[j + 1] == redo[j] + 1 && (int64_t)(j + 1 - i) < Fb) ++j;
             const int c0 = redo[i], fb = (int)(j - i + 1);
             CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + (int64_t)c0 * col_stride,
-                                    d_out + (int64_t)c0 * col_stride, col_stride, ghist, gbase, status, tiles));
+                                    d_out + (int64_t)c0 * col_stride, col_stride, ghist, gbase, status, tiles, nullptr,
+                                    false));
             i = j + 1;
         }
         return 0;
@@ -491,7 +600,7 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
     for (int64_t c0 = 0; c0 < F; c0 += Fb) {
         const int fb = (int)(F - c0 < Fb ? F - c0 : Fb);
         CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + c0 * col_stride,
-                                d_out + c0 * col_stride, col_stride, ghist, gbase, status, tiles));
+                                d_out + c0 * col_stride, col_stride, ghist, gbase, status, tiles, nullptr, false));
     }
     return 0;
 }
