@@ -86,9 +86,9 @@ with open(os.path.join(out_dir, f"{tag}_ncu_full_summary.md"), "w") as f:
         rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
         wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
         traffic[name].append(rd + wr)
-cls = {"radix_pass_kernel<0, 0>": "sort_radix_pass", "l2_scan_kernel": "l2_scan_search",
+cls = {"radix_pass_kernel<unsigned int, 0, 0>": "sort_radix_pass", "l2_scan_stream_kernel": "l2_scan_search",
        "partition_kernel": "partition", "sort_prepare_kernel": "sort_prepare",
-       "gather_payload_kernel": "gather_y_payload"}
+       "gather_payload_kernel": "gather_y_payload", "sort_fixup_kernel": "sort_fixup_ties"}
 tj = {}
 for name, vals in traffic.items():
     for k, c in cls.items():
