@@ -103,6 +103,23 @@ int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int
                int64_t *children_right, int64_t *feature, double *threshold, double *value,
                int64_t capacity, int64_t *node_count);
 
+/* Same fit with the conventions of the reference's level-synchronous builder:
+ * replaces: four.build_regression_tree(X, y, max_depth, min_improvement, min_sample_leaf)
+ *                                                                    ref four.py:108-172
+ * flags: B200DT_NUMBER_BY_LEVEL -- node ids level by level, inside a level all LEFT children of the
+ *        previous level's split nodes (in their order) and then all RIGHT children (four.py:113-170:
+ *        sizes = left_sizes + right_sizes, ids handed out in that order, four.py:84-89);
+ *        B200DT_LEAF_IF_LE -- a node is a leaf when its best gain is <= min_improvement
+ *        (four.py:143; one.py:150 uses <).
+ * n_node_samples (may be NULL): rows of every node, int32 like the reference (four.py:69,91-92). */
+#define B200DT_NUMBER_BY_LEVEL 1
+#define B200DT_LEAF_IF_LE 2
+int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F,
+                  int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
+                  int64_t min_sample_leaf, int variant, int flags, int64_t *children_left,
+                  int64_t *children_right, int64_t *feature, double *threshold, double *value,
+                  int32_t *n_node_samples, int64_t capacity, int64_t *node_count);
+
 /* ---- feature-sharded fit: one session per GPU, driven level by level --------------
  * The host loop of ref one.py:141-160, level-synchronous.  Each rank owns columns
  * [col_offset, col_offset + F_local) of a global (N, F_global) matrix; X points at the

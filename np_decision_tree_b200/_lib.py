@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libb200tree.so")
 
 HOST, DEVICE = 0, 1
 L2, L1 = 0, 1
+NUMBER_BY_LEVEL, LEAF_IF_LE = 1, 2
 
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
@@ -50,6 +51,8 @@ _SIGNATURES = {
     "b200dt_split_orders": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "b200dt_fit": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_i64,
                            c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
+    "b200dt_fit_ex": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_i64,
+                              c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "b200dt_session_begin": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl,
                                      c_i64, c_int, c_i64, c_i64, c_vp, c_i64]),
     "b200dt_session_live": (c_int, [c_vp, ctypes.POINTER(c_i64)]),

@@ -446,7 +446,9 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             score_for_test = w.gain;
         else
             score_for_test = w.gain * w.gain;  // one.py:93 returns the square of the best ratio score
-        if (score_for_test < s->min_improvement) {  // one.py:150
+        const bool stop = (s->flags & B200DT_LEAF_IF_LE) ? score_for_test <= s->min_improvement   // four.py:143
+                                                         : score_for_test < s->min_improvement;   // one.py:150
+        if (stop) {
             HNode &nd = s->nodes[nid];
             nd.leaf = true;
             nd.value = nd.total / (double)nd.n;
@@ -594,7 +596,8 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
 }
 
 static int session_finish_impl(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
-                               double *threshold, double *value, int64_t capacity, int64_t *node_count) {
+                               double *threshold, double *value, int32_t *n_node_samples, int64_t capacity,
+                               int64_t *node_count) {
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     if (!s->live.empty()) return ctx->fail_msg("session: finish called before the tree is complete");
@@ -605,18 +608,35 @@ static int session_finish_impl(b200dt_ctx *ctx, int64_t *children_left, int64_t 
     }
     const int64_t count = (int64_t)s->nodes.size();
     if (count > capacity) return ctx->fail_msg("fit: tree arrays too small");
-    // pre-order ids, left first (one.py:26-31: ids are handed out as tasks are popped;
-    // one.py:157-160: right is pushed first so left is popped first)
-    std::vector<int> new_id(count, -1), stack;
-    stack.push_back(0);
-    int next = 0;
-    while (!stack.empty()) {
-        const int v = stack.back();
-        stack.pop_back();
-        new_id[v] = next++;
-        if (!s->nodes[v].leaf) {
-            stack.push_back(s->nodes[v].right);
-            stack.push_back(s->nodes[v].left);
+    std::vector<int> new_id(count, -1);
+    if (s->flags & B200DT_NUMBER_BY_LEVEL) {
+        // four.py:113-170: a level is processed as [left children of the previous level's split nodes,
+        // in their order] + [their right children]; ids are handed out in processing order
+        std::vector<int> level(1, 0), next_level;
+        int next = 0;
+        while (!level.empty()) {
+            for (int v : level) new_id[v] = next++;
+            next_level.clear();
+            for (int v : level)
+                if (!s->nodes[v].leaf) next_level.push_back(s->nodes[v].left);
+            for (int v : level)
+                if (!s->nodes[v].leaf) next_level.push_back(s->nodes[v].right);
+            level.swap(next_level);
+        }
+    } else {
+        // pre-order ids, left first (one.py:26-31: ids are handed out as tasks are popped;
+        // one.py:157-160: right is pushed first so left is popped first)
+        std::vector<int> stack;
+        stack.push_back(0);
+        int next = 0;
+        while (!stack.empty()) {
+            const int v = stack.back();
+            stack.pop_back();
+            new_id[v] = next++;
+            if (!s->nodes[v].leaf) {
+                stack.push_back(s->nodes[v].right);
+                stack.push_back(s->nodes[v].left);
+            }
         }
     }
     for (int64_t v = 0; v < count; ++v) {
@@ -634,6 +654,7 @@ static int session_finish_impl(b200dt_ctx *ctx, int64_t *children_left, int64_t 
             threshold[id] = nd.thr;
         }
         value[id] = nd.value;
+        if (n_node_samples) n_node_samples[id] = nd.n;
     }
     *node_count = count;
     return 0;
@@ -770,19 +791,21 @@ int b200dt_session_partition(b200dt_ctx *ctx, const uint32_t *d_side_mask) {
 int b200dt_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
                           double *threshold, double *value, int64_t capacity, int64_t *node_count) {
     CK(cudaSetDevice(ctx->device));
-    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, capacity, node_count);
+    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, nullptr, capacity,
+                                node_count);
     session_free(ctx);
     return r;
 }
 
-int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F, int64_t ldx, int space,
-               int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant,
-               int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
-               int64_t capacity, int64_t *node_count) {
+int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F, int64_t ldx, int space,
+                  int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant, int flags,
+                  int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
+                  int32_t *n_node_samples, int64_t capacity, int64_t *node_count) {
     CK(cudaSetDevice(ctx->device));
     CKR(session_begin_impl(ctx, X, y, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf,
                            variant, 0, F, nullptr, 0));
     Session *s = ctx->session;
+    s->flags = flags;
     while (!s->live.empty()) {
         const int n_live = (int)s->live.size();
         CKR(scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(b200dt_candidate) + 64, (void **)&s->d_cand));
@@ -796,9 +819,18 @@ int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int
         }
         if (need_part) CKR(session_partition_impl(ctx, s->d_own_mask));
     }
-    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, capacity, node_count);
+    int r = session_finish_impl(ctx, children_left, children_right, feature, threshold, value, n_node_samples,
+                                capacity, node_count);
     session_free(ctx);
     return r;
+}
+
+int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F, int64_t ldx, int space,
+               int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant,
+               int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
+               int64_t capacity, int64_t *node_count) {
+    return b200dt_fit_ex(ctx, X, y, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf, variant,
+                         0, children_left, children_right, feature, threshold, value, nullptr, capacity, node_count);
 }
 
 // ---- single-node ops (parity tests of K1 / K2 / K4) --------------------------------------

@@ -49,6 +49,7 @@ struct Session {
     std::vector<SegDev> plan_segs;
     std::vector<PlanSeg> plan_fused;   // same nodes, for the fused level kernel (payload sessions)
     std::vector<TileDesc> plan_tiles;
+    int flags = 0;             // B200DT_NUMBER_BY_LEVEL | B200DT_LEAF_IF_LE (four.py conventions)
     bool fuse_levels = false;  // B200DT_FUSE=1: partition + search of the children in one kernel (fused.cu)
     int fused_slots = 0;       // candidate slots of the CURRENT level written by the fused kernel
     int next_fused_slots = 0;  // ... of the level being planned

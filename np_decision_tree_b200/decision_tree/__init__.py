@@ -1,2 +1,2 @@
 """Mirror of the reference package ``decision_tree`` (hot-path modules only)."""
-from . import one, strategy_l1, utils, np_stream_median  # noqa: F401
+from . import one, strategy_l1, utils, np_stream_median, four  # noqa: F401

@@ -32,4 +32,7 @@ from .np_tree_oracle import (  # noqa: F401
     fit_l1,
     predict,
     predict_leaf,
+    LevelTreeArrays,
+    l2_best_split_weighted,
+    fit_l2_levelwise,
 )

@@ -359,3 +359,95 @@ def predict(data, tree):
 def predict_leaf(data, tree):
     """ref: decision_tree/utils.py:34-48 (inference_leaf)."""
     return _descend(data, tree)
+
+
+# --------------------------------------------------------------------------
+# level-synchronous builder with optional sample weights (SURVEY section 8f, rank 2)
+# --------------------------------------------------------------------------
+LevelTreeFields = namedtuple(
+    "LevelTreeFields", "children_left children_right feature threshold value n_node_samples")
+
+
+class LevelTreeArrays:
+    """ref: decision_tree/four.py:61-98 -- the one.py container plus int32 n_node_samples (-2 = unused)."""
+
+    def __init__(self, max_depth):
+        slots = 2 ** (max_depth + 1) - 1
+        self.tree_ = LevelTreeFields(
+            np.full(slots, -1, dtype=np.int64), np.full(slots, -1, dtype=np.int64),
+            np.full(slots, -2, dtype=np.int64), np.full(slots, -2.0, dtype=np.float64),
+            np.full(slots, np.nan, dtype=np.float64), np.full(slots, -2, dtype=np.int32))
+        self.max_node_ = -1
+
+    @property
+    def node_count(self):
+        return self.max_node_ + 1
+
+    def leaf_mask(self):
+        m = np.zeros(self.tree_.feature.shape[0], dtype=bool)
+        m[: self.node_count] = self.tree_.children_left[: self.node_count] == -1
+        return m
+
+
+def l2_best_split_weighted(ys, ws):
+    """Weighted search: ys = (y*w)[orders], ws = w[orders] of one node.
+
+    ref: decision_tree/four.py:21-30.  Flat row-major argmax => lowest position, then feature."""
+    sum_y = np.cumsum(ys, axis=0)
+    sum_w = np.cumsum(ws, axis=0)
+    expected = sum_w * sum_y[-1][-1] / sum_w[-1][-1]
+    sq = np.square(sum_y - expected)
+    ratio = np.reciprocal(sum_w[:-1] * (sum_w[-1][-1] - sum_w[:-1]))
+    gain = ratio * sq[:-1]
+    k, f = np.unravel_index(np.argmax(gain), gain.shape)
+    return k, f, gain[k, f]
+
+
+def fit_l2_levelwise(X, y, max_depth=2, min_improvement=1e-7, min_sample_leaf=1, weight=None,
+                     sort_kind=None):
+    """ref: decision_tree/four.py:108-172 (build_regression_tree).
+
+    Differences from one.py kept: node ids level by level -- all left children of a level, then
+    all right children (four.py:113,162-170) --, leaf when gain <= min_improvement (four.py:143),
+    n_node_samples, leaf = mean over column 0's order (four.py:130,145), weights multiply y once
+    (four.py:116-117) and leaf = sum(y w) / sum(w) (four.py:132-133)."""
+    tree = LevelTreeArrays(max_depth)
+    t = tree.tree_
+    n_samples = X.shape[0]
+    yw = y * weight if weight is not None else y
+    level = [(argsort_columns(X, kind=sort_kind), None, True)]
+    for depth in range(max_depth + 1):
+        lefts, rights = [], []
+        for orders, parent, is_left in level:
+            tree.max_node_ += 1
+            node = tree.max_node_
+            if parent is not None:
+                (t.children_left if is_left else t.children_right)[parent] = node
+            n = orders.shape[0]
+            t.n_node_samples[node] = n
+            ys = yw[orders]
+            ws = weight[orders] if weight is not None else None
+
+            def leaf():
+                if ws is None:
+                    t.value[node] = np.mean(ys[:, 0])
+                else:
+                    t.value[node] = np.sum(ys[:, 0]) / np.sum(ws[:, 0])
+
+            if n <= min_sample_leaf or depth >= max_depth:
+                leaf()
+                continue
+            if ws is None:
+                k, f, gain = l2_best_split(np.cumsum(ys, axis=0))     # four.py:11-20 == one.py:56-63
+            else:
+                k, f, gain = l2_best_split_weighted(ys, ws)
+            if gain <= min_improvement:
+                leaf()
+                continue
+            t.feature[node] = f
+            t.threshold[node] = X[orders[k, f], f]
+            lo, ro = partition_orders(orders, orders[: k + 1, f], n_samples)
+            lefts.append((lo, node, True))
+            rights.append((ro, node, False))
+        level = lefts + rights
+    return tree

@@ -115,3 +115,26 @@ def test_predict_root_only_shape_quirk(golden_small):
     g = golden_small
     t = oracle.fit_l2(g["l2_s7_X"], g["l2_s7_y"], max_depth=0)
     assert oracle.predict(g["l2_s7_X"], t).shape == (1,) == g["l2_s7_pred"].shape
+
+
+LEVEL_CASES = ["u0", "u1", "u2", "u3", "w0", "w1", "w2"]
+
+
+@pytest.mark.parametrize("name", LEVEL_CASES)
+def test_levelwise_tree_small(golden_small, name):
+    """ref four.py: level-synchronous builder, unweighted (u*) and weighted (w*)."""
+    g = golden_small
+    X, y, depth = g[f"lv_{name}_X"], g[f"lv_{name}_y"], int(g[f"lv_{name}_depth"])
+    w = g[f"lv_{name}_w"] if f"lv_{name}_w" in g.files else None
+    t = oracle.fit_l2_levelwise(X, y, max_depth=depth, weight=w)
+    assert_same_tree(t, GoldenTree(g, f"lv_{name}_"), leaf_rtol=0.0, what=name)
+    assert np.array_equal(t.tree_.n_node_samples, g[f"lv_{name}_n_node_samples"])
+    assert t.tree_.n_node_samples.dtype == np.int32
+
+
+def test_levelwise_knobs(golden_small):
+    g = golden_small
+    t = oracle.fit_l2_levelwise(g["lv_knobs_X"], g["lv_knobs_y"], max_depth=5, min_improvement=200.0,
+                                min_sample_leaf=30)
+    assert_same_tree(t, GoldenTree(g, "lv_knobs_"), leaf_rtol=0.0)
+    assert np.array_equal(t.tree_.n_node_samples, g["lv_knobs_n_node_samples"])
