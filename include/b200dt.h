@@ -111,11 +111,15 @@ int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int
  *        sizes = left_sizes + right_sizes, ids handed out in that order, four.py:84-89);
  *        B200DT_LEAF_IF_LE -- a node is a leaf when its best gain is <= min_improvement
  *        (four.py:143; one.py:150 uses <).
- * n_node_samples (may be NULL): rows of every node, int32 like the reference (four.py:69,91-92). */
+ * n_node_samples (may be NULL): rows of every node, int32 like the reference (four.py:69,91-92).
+ * weight (may be NULL): (N,) float64 sample weights, same space as X / y (four.py:116-117, 21-30:
+ *   y <- y*w once, gain = (sum_yw - sum_w * T_yw / T_w)^2 / (sum_w (T_w - sum_w)), flat (k, f) argmax,
+ *   leaf = sum(y w) / sum(w)); L2, variant 1 only. */
 #define B200DT_NUMBER_BY_LEVEL 1
 #define B200DT_LEAF_IF_LE 2
-int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F,
-                  int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
+int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, const double *weight,
+                  int64_t N, int64_t F, int64_t ldx, int space, int criterion, int max_depth,
+                  double min_improvement,
                   int64_t min_sample_leaf, int variant, int flags, int64_t *children_left,
                   int64_t *children_right, int64_t *feature, double *threshold, double *value,
                   int32_t *n_node_samples, int64_t capacity, int64_t *node_count);

@@ -137,7 +137,7 @@ static bool node_is_leaf_by_size(const Session *s, const HNode &nd) {
 static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F_local,
                               int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
                               int64_t min_sample_leaf, int variant, int64_t col_offset, int64_t F_global,
-                              const double *last_col, int64_t last_col_ld) {
+                              const double *last_col, int64_t last_col_ld, const double *weight = nullptr) {
     if (N <= 0 || F_local <= 0) return ctx->fail_msg("fit: empty input");
     if (N >= (1ll << 30)) return ctx->fail_msg("fit: N must be < 2^30");
     if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit: max_depth out of range [0, 30]");
@@ -206,6 +206,25 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         s->ldx = ldx;
         s->dy = y;
     }
+    if (weight) {
+        if (criterion != B200DT_L2 || variant != 1)
+            return ctx->fail_msg("fit: sample weights are defined for the L2 criterion (v == 1) only");
+        // four.py:116-117: y <- y * weight once; the search then works on (y*w, w)
+        const double *dw = weight;
+        if (space == B200DT_HOST) {
+            double *buf;
+            CKR(scratch_get(ctx, SB_W, (size_t)N * 8, (void **)&buf));
+            CK(cudaMemcpyAsync(buf, weight, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+            // y travels on the copy stream, ahead of the first X batch: wait for that batch's event
+            if (n_h2d > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[0], 0));
+            dw = buf;
+        }
+        double *yw;
+        CKR(scratch_get(ctx, SB_YW, (size_t)N * 8, (void **)&yw));
+        CKR(launch_mul(ctx, s->dy, dw, N, yw));
+        s->dy = yw;
+        s->dw = dw;
+    }
     CKR(scratch_get(ctx, SB_ORD_A, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[0]));
     CKR(scratch_get(ctx, SB_ORD_B, (size_t)F_store * s->col_stride * 4, (void **)&s->ord[1]));
     s->cur = 0;
@@ -253,6 +272,11 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
                                 s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
     }
     if (s->ypay[0]) CKR(launch_gather_payload(ctx, s->ord[0], s->dy, s->ypay[0], s->col_stride, F_store, N));
+    if (s->dw) {
+        CKR(scratch_get(ctx, SB_WPAY0, (size_t)kcap * 8, (void **)&s->wpay[0]));
+        CKR(scratch_get(ctx, SB_WPAY1, (size_t)kcap * 8, (void **)&s->wpay[1]));
+        CKR(launch_gather_payload(ctx, s->ord[0], s->dw, s->wpay[0], s->col_stride, F_store, N));
+    }
     // (the look-back status arrays are sized per launch from the actual tile count)
     CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
 
@@ -260,13 +284,14 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     root.start = 0;
     root.n = (int)N;
     CKR(device_sum(ctx, s->dy, N, &root.total));
+    if (s->dw) CKR(device_sum(ctx, s->dw, N, &root.total_w));
     s->nodes.clear();
     s->nodes.push_back(root);
     s->live.clear();
     s->depth = 0;
     if (node_is_leaf_by_size(s, s->nodes[0])) {
         s->nodes[0].leaf = true;
-        s->nodes[0].value = root.total / (double)N;
+        s->nodes[0].value = s->dw ? root.total / root.total_w : root.total / (double)N;
         if (criterion == B200DT_L1) s->median_pending_cur.push_back(0);
     } else {
         s->live.push_back(0);
@@ -287,12 +312,13 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     // them every live node reserves slots of its own (its tiles when it must be scanned here -- the
     // root, or any node of a gather-path session -- else one, for the sequential search)
     int pbase = s->fused_slots;
-    const int scan_tile = l2_scan_tile(s->ypay[0] != nullptr);
+    const int scan_tile = s->dw ? WT_TILE : l2_scan_tile(s->ypay[0] != nullptr);
     for (int i = 0; i < n_live; ++i) {
         const HNode &nd = s->nodes[s->live[i]];
         const int ntiles = (nd.n + scan_tile - 1) / scan_tile;
         SegDev sg;
         sg.total = nd.total;
+        sg.total_w = nd.total_w;
         sg.start = nd.start;
         sg.n = nd.n;
         sg.nleft = 0;
@@ -357,31 +383,44 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     a.ypay = s->ypay[s->cur];
     a.segs = s->d_segs;
     a.n_segs = n_live;
-    // look-back status: one entry per (tile, column); a freshly (re)allocated buffer is zeroed,
-    // which no epoch ever matches
-    ScanStatus st;
-    const size_t n_status = tiles.size() * (size_t)s->F_local + 1;
-    CKR(scratch_get(ctx, SB_STATUS_F, n_status * 16, (void **)&st.slot, true));
-    u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
-    CKR(next_epoch(ctx));
-    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
-    CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
-                        s->d_partials, s->variant));
+    a.wpay = s->wpay[s->cur];
     int64_t max_records = 0;
     for (const SegDev &sg : s->h_segs) max_records = std::max<int64_t>(max_records, (int64_t)sg.np * s->F_local);
     Partial *d_sliced;
     CKR(scratch_get(ctx, SB_L1_G, (size_t)n_live * FIN_SLICES_HOST * sizeof(Partial) + 64, (void **)&d_sliced));
+    // look-back status: one entry per (tile, column); a freshly (re)allocated buffer is zeroed,
+    // which no epoch ever matches
+    const size_t n_status = tiles.size() * (size_t)s->F_local + 1;
+    u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
+    CKR(next_epoch(ctx));
+    if (s->dw) {
+        // weighted search (four.py:21-30): two payload channels, flat (k, f) tie rule
+        u64 *st3;
+        double *d_tw;
+        CKR(scratch_get(ctx, SB_STATUS_F, n_status * 48, (void **)&st3, true));
+        CKR(scratch_get(ctx, SB_TW, (size_t)n_live * 8 + 64, (void **)&d_tw));
+        CKR(launch_l2w_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st3, ctx->epoch, s->d_partials));
+        CKR(launch_l2w_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total, d_tw,
+                             s->d_partials));
+        CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out, true));
+        return 0;
+    }
+    ScanStatus st;
+    CKR(scratch_get(ctx, SB_STATUS_F, n_status * 16, (void **)&st.slot, true));
+    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
+    CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
+                        s->d_partials, s->variant));
     CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out));
     return 0;
 }
 
 // winner of one node among the ranks' candidates: (score desc, k asc, aux desc, f asc)
-static bool cand_better(const b200dt_candidate &b, const b200dt_candidate &a) {
+static bool cand_better(const b200dt_candidate &b, const b200dt_candidate &a, bool flat) {
     if (b.k < 0) return false;
     if (a.k < 0) return true;
     if (b.gain != a.gain) return b.gain > a.gain;
     if (b.k != a.k) return b.k < a.k;
-    if (b.aux != a.aux) return b.aux > a.aux;
+    if (!flat && b.aux != a.aux) return b.aux > a.aux;   // flat argmax criteria carry data in aux
     return b.f < a.f;
 }
 
@@ -406,7 +445,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
         for (int r = 1; r < n_ranks; ++r) {
             const b200dt_candidate &c = h[(size_t)r * n_live + i];
             second = std::max(second, c.gain2);
-            if (cand_better(c, best)) {
+            if (cand_better(c, best, s->dw != nullptr)) {
                 if (best.k >= 0) second = std::max(second, best.gain);
                 best = c;
             } else if (c.k >= 0) {
@@ -435,7 +474,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     s->plan_tiles.clear();
     s->plan_elems = 0;
     s->next_fused_slots = 0;
-    const bool payload = s->ypay[0] != nullptr && s->fuse_levels;
+    const bool payload = s->ypay[0] != nullptr && s->fuse_levels && !s->dw;
     for (int i = 0; i < n_live; ++i) {
         const int nid = s->live[i];
         const b200dt_candidate &w = win[i];
@@ -451,18 +490,22 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
         if (stop) {
             HNode &nd = s->nodes[nid];
             nd.leaf = true;
-            nd.value = nd.total / (double)nd.n;
+            nd.value = s->dw ? nd.total / nd.total_w : nd.total / (double)nd.n;
             if (s->criterion == B200DT_L1) s->median_pending_cur.push_back(nid);
             continue;
         }
         const int start = s->nodes[nid].start, n = s->nodes[nid].n;
-        const double total = s->nodes[nid].total;
+        const double total = s->nodes[nid].total, total_w = s->nodes[nid].total_w;
         const int nl = w.k + 1;
         s->nodes[nid].feature = w.f;
         s->nodes[nid].thr = w.threshold;
-        s->nodes[nid].value = total / (double)n;
+        s->nodes[nid].value = s->dw ? total / total_w : total / (double)n;
         const int lc = make_child(s, nid, 1, start, nl, w.left_sum);
         const int rc = make_child(s, nid, 0, start + nl, n - nl, total - w.left_sum);
+        if (s->dw) {   // weighted: the candidate's aux slot is the left weight sum
+            s->nodes[lc].total_w = w.aux;
+            s->nodes[rc].total_w = total_w - w.aux;
+        }
         s->nodes[nid].left = lc;
         s->nodes[nid].right = rc;
         bool any_search = false;
@@ -470,7 +513,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             HNode &ch = s->nodes[c];
             if (node_is_leaf_by_size(s, ch)) {
                 ch.leaf = true;
-                ch.value = ch.total / (double)ch.n;
+                ch.value = s->dw ? ch.total / ch.total_w : ch.total / (double)ch.n;
                 if (s->criterion == B200DT_L1) s->median_pending_next.push_back(c);
             } else {
                 next_live.push_back(c);
@@ -481,6 +524,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
         if (any_search || s->criterion == B200DT_L1) {
             SegDev sg;
             sg.total = 0.0;
+            sg.total_w = 0.0;
             sg.start = start;
             sg.n = n;
             sg.pbase = 0;
@@ -566,7 +610,7 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
     u64 *pstatus;
-    if (s->ypay[0] && s->fuse_levels && s->plan_fused.size() == s->plan_segs.size()) {
+    if (s->ypay[0] && s->fuse_levels && !s->dw && s->plan_fused.size() == s->plan_segs.size()) {
         // streaming path: partition (row, y) and search the children in the same pass
         PlanSeg *d_plan;
         const size_t plan_bytes = s->plan_fused.size() * sizeof(PlanSeg);
@@ -585,7 +629,7 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
         CKR(next_epoch(ctx));
         CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
                              (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket,
-                             s->ypay[s->cur], s->ypay[s->cur ^ 1]));
+                             s->ypay[s->cur], s->ypay[s->cur ^ 1], s->wpay[s->cur], s->wpay[s->cur ^ 1]));
     }
     s->cur ^= 1;
     s->plan_segs.clear();
@@ -797,13 +841,14 @@ int b200dt_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *chil
     return r;
 }
 
-int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int64_t F, int64_t ldx, int space,
-                  int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant, int flags,
+int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, const double *weight, int64_t N, int64_t F,
+                  int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
+                  int64_t min_sample_leaf, int variant, int flags,
                   int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
                   int32_t *n_node_samples, int64_t capacity, int64_t *node_count) {
     CK(cudaSetDevice(ctx->device));
     CKR(session_begin_impl(ctx, X, y, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf,
-                           variant, 0, F, nullptr, 0));
+                           variant, 0, F, nullptr, 0, weight));
     Session *s = ctx->session;
     s->flags = flags;
     while (!s->live.empty()) {
@@ -829,8 +874,9 @@ int b200dt_fit(b200dt_ctx *ctx, const double *X, const double *y, int64_t N, int
                int criterion, int max_depth, double min_improvement, int64_t min_sample_leaf, int variant,
                int64_t *children_left, int64_t *children_right, int64_t *feature, double *threshold, double *value,
                int64_t capacity, int64_t *node_count) {
-    return b200dt_fit_ex(ctx, X, y, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf, variant,
-                         0, children_left, children_right, feature, threshold, value, nullptr, capacity, node_count);
+    return b200dt_fit_ex(ctx, X, y, nullptr, N, F, ldx, space, criterion, max_depth, min_improvement, min_sample_leaf,
+                         variant, 0, children_left, children_right, feature, threshold, value, nullptr, capacity,
+                         node_count);
 }
 
 // ---- single-node ops (parity tests of K1 / K2 / K4) --------------------------------------
@@ -997,6 +1043,7 @@ int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64
     CK(cudaMemcpyAsync(s->d_own_mask, hmask.data(), hmask.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     SegDev sg;
     sg.total = 0.0;
+    sg.total_w = 0.0;
     sg.start = 0;
     sg.n = (int)n;
     sg.pbase = 0;

@@ -373,6 +373,7 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
         segs[i] = L1Seg{nd.start, nd.n};
         SegDev sg;
         sg.total = 0.0;
+        sg.total_w = 0.0;
         sg.start = nd.start;
         sg.n = nd.n;
         sg.pbase = i;
@@ -435,6 +436,7 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
     a.F_search = F;
     a.y = s->dy;
     a.ypay = nullptr;
+    a.wpay = nullptr;
     a.segs = s->d_segs;
     a.n_segs = n_live;
     CKR(launch_finalize(ctx, a, s->d_partials, F, nullptr, s->dX, s->ldx, s->col_offset, d_out));

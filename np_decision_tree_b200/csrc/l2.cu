@@ -348,17 +348,21 @@ __global__ void __launch_bounds__(256) l2_exact_kernel(LevelArgs a, const int *_
 // (score desc, k asc, aux desc, f asc): within one sorted position the reference compares
 // |S-(k+1)mean| across features (one.py:59) and across positions the weighted squares
 // (one.py:62); aux is 0 for the other criteria, which then tie-break on (k, f) only.
+// FLAT: the criteria that take a flat row-major argmax (four.py:28, one.py:91, strategy_l1.py:120)
+// break ties on (k, f) only; there the aux slot carries data (the left weight sum), not a tie key.
+template <bool FLAT>
 __device__ __forceinline__ bool partial_better(const Partial &b, const Partial &a) {
     if (b.k < 0) return false;
     if (a.k < 0) return true;
     if (b.score != a.score) return b.score > a.score;
     if (b.k != a.k) return b.k < a.k;
-    if (b.aux != a.aux) return b.aux > a.aux;
+    if (!FLAT && b.aux != a.aux) return b.aux > a.aux;
     return b.f < a.f;
 }
 
+template <bool FLAT>
 __device__ __forceinline__ void partial_merge(Partial &a, const Partial &b) {
-    const bool bw = partial_better(b, a);
+    const bool bw = partial_better<FLAT>(b, a);
     const double loser = bw ? (a.k < 0 ? -CUDART_INF : a.score) : (b.k < 0 ? -CUDART_INF : b.score);
     const double s2 = fmax(fmax(a.score2, b.score2), loser);
     if (bw) a = b;
@@ -376,6 +380,7 @@ __device__ __forceinline__ Partial partial_none() {
     return b;
 }
 
+template <bool FLAT>
 __device__ __forceinline__ Partial partial_block_reduce(Partial b, Partial *sp) {
     const int tid = threadIdx.x;
     sp[tid] = b;
@@ -383,7 +388,7 @@ __device__ __forceinline__ Partial partial_block_reduce(Partial b, Partial *sp) 
     for (int s = 64; s >= 1; s >>= 1) {
         if (tid < s) {
             Partial mine = sp[tid];
-            partial_merge(mine, sp[tid + s]);
+            partial_merge<FLAT>(mine, sp[tid + s]);
             sp[tid] = mine;
         }
         __syncthreads();
@@ -394,6 +399,7 @@ __device__ __forceinline__ Partial partial_block_reduce(Partial b, Partial *sp) 
 constexpr int FIN_SLICES = 64;  // stage-1 blocks per node with many candidates
 
 // stage 1: blockIdx.y = node, blockIdx.x = slice of that node's (tiles x columns) candidates
+template <bool FLAT>
 __global__ void __launch_bounds__(128) finalize_slices_kernel(LevelArgs a, const Partial *__restrict__ partials,
                                                               Partial *__restrict__ sliced) {
     __shared__ Partial sp[128];
@@ -403,13 +409,14 @@ __global__ void __launch_bounds__(128) finalize_slices_kernel(LevelArgs a, const
     Partial b = partial_none();
     for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < count; r += (int64_t)FIN_SLICES * 128) {
         const int64_t j = r / a.F_search, f = r - j * a.F_search;
-        partial_merge(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
+        partial_merge<FLAT>(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
     }
-    b = partial_block_reduce(b, sp);
+    b = partial_block_reduce<FLAT>(b, sp);
     if (threadIdx.x == 0) sliced[(int64_t)seg * FIN_SLICES + blockIdx.x] = b;
 }
 
 // stage 2 (or the only stage when `sliced` is null): one block per node
+template <bool FLAT>
 __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partial *__restrict__ partials,
                                                        const Partial *__restrict__ sliced,
                                                        const double *__restrict__ X, int64_t ldx, int col_offset,
@@ -420,15 +427,15 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
     const int tid = threadIdx.x;
     Partial b = partial_none();
     if (sliced) {
-        for (int r = tid; r < FIN_SLICES; r += 128) partial_merge(b, sliced[(int64_t)seg * FIN_SLICES + r]);
+        for (int r = tid; r < FIN_SLICES; r += 128) partial_merge<FLAT>(b, sliced[(int64_t)seg * FIN_SLICES + r]);
     } else {
         const int64_t count = (int64_t)sg.np * a.F_search;
         for (int64_t r = tid; r < count; r += 128) {
             const int64_t j = r / a.F_search, f = r - j * a.F_search;
-            partial_merge(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
+            partial_merge<FLAT>(b, partials[(sg.pbase + j * sg.pstep + sg.pside) * a.F_search + f]);
         }
     }
-    const Partial w = partial_block_reduce(b, sp);
+    const Partial w = partial_block_reduce<FLAT>(b, sp);
     if (tid == 0) {
         b200dt_candidate c;
         c.gain = w.score;
@@ -507,16 +514,23 @@ int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, 
 }
 
 int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, int64_t max_records,
-                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out) {
+                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out,
+                    bool flat_rule) {
     if (a.n_segs <= 0) return 0;
     const Partial *stage1 = nullptr;
     if (max_records > 64 * 1024 && sliced) {
         LaunchScope ls(ctx, KC_FINALIZE, 0.0);
-        finalize_slices_kernel<<<dim3(FIN_SLICES, a.n_segs), 128, 0, ctx->stream>>>(a, partials, sliced);
+        if (flat_rule)
+            finalize_slices_kernel<true><<<dim3(FIN_SLICES, a.n_segs), 128, 0, ctx->stream>>>(a, partials, sliced);
+        else
+            finalize_slices_kernel<false><<<dim3(FIN_SLICES, a.n_segs), 128, 0, ctx->stream>>>(a, partials, sliced);
         stage1 = sliced;
     }
     LaunchScope ls(ctx, KC_FINALIZE, 0.0);
-    finalize_kernel<<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, stage1, X, ldx, col_offset, out);
+    if (flat_rule)
+        finalize_kernel<true><<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, stage1, X, ldx, col_offset, out);
+    else
+        finalize_kernel<false><<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, stage1, X, ldx, col_offset, out);
     CK(cudaGetLastError());
     return 0;
 }

@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // One warp owns one tile of PT_TILE positions of one (node, column).  Every lane sees every
 // ballot, so the running left-count of the tile lives in registers: no shared memory, no
 // block barrier.  Persistent grid, static tile-major order (see l2.cu).
-template <bool PAY>
+template <int PAY>
 __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                            const double *__restrict__ y_in, double *__restrict__ y_out,
+                                                           const double *__restrict__ w_in, double *__restrict__ w_out,
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
                                                            const u32 *__restrict__ mask, u64 *status, u32 epoch,
@@ -72,14 +73,17 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         int *ocol = out + cbase;
         const double *ycol = PAY ? y_in + cbase + off : nullptr;
         double *oy = PAY ? y_out + cbase : nullptr;
+        const double *wcol = PAY == 2 ? w_in + cbase + off : nullptr;
+        double *ow = PAY == 2 ? w_out + cbase : nullptr;
 #pragma unroll
         for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
-            double yv[4];
+            double yv[4], wv[4];
             if (PAY) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int e = (i0 + u) * 32 + lane;
                     yv[u] = e < cnt ? __ldcs(ycol + e) : 0.0;
+                    if (PAY == 2) wv[u] = e < cnt ? __ldcs(wcol + e) : 0.0;
                 }
             }
 #pragma unroll
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                     const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
                     ocol[dest] = rows[i];
                     if (PAY) oy[dest] = yv[u];
+                    if (PAY == 2) ow[dest] = wv[u];
                 }
                 lb_row += __popc(b);
             }
@@ -118,22 +123,23 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
-                     u64 *status, u32 epoch, u32 *ticket, const double *y_in, double *y_out) {
+                     u64 *status, u32 epoch, u32 *ticket, const double *y_in, double *y_out, const double *w_in,
+                     double *w_out) {
     (void)ticket;
     if (n_tiles <= 0) return 0;
-    const bool pay = y_in != nullptr && y_out != nullptr;
+    const int pay = (y_in && y_out) ? ((w_in && w_out) ? 2 : 1) : 0;
     const int64_t total = (int64_t)n_tiles * F_store;
     int per_sm = 0;
-    const void *kern = pay ? (const void *)partition_kernel<true> : (const void *)partition_kernel<false>;
+    const void *kern = pay == 2 ? (const void *)partition_kernel<2>
+                                : pay == 1 ? (const void *)partition_kernel<1> : (const void *)partition_kernel<0>;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
-    const double *yi = pay ? y_in : nullptr;
-    double *yo = pay ? y_out : nullptr;
-    void *args[] = {&orders_in, &orders_out, &yi, &yo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status, &epoch,
-                    &F_store};
+    const double *yi = pay ? y_in : nullptr, *wi = pay == 2 ? w_in : nullptr;
+    double *yo = pay ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;
+    void *args[] = {&orders_in, &orders_out, &yi, &yo, &wi, &wo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status,
+                    &epoch, &F_store};
     CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
-    CK(cudaGetLastError());
     return 0;
 }

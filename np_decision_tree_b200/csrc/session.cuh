@@ -11,6 +11,7 @@ struct HNode {
     int start = 0;
     int n = 0;
     double total = 0.0;
+    double total_w = 0.0;   // weighted fits: sum of the weights of the node (total is then sum of y*w)
     int feature = -2;
     double thr = -2.0;
     int left = -1, right = -1;
@@ -32,6 +33,8 @@ struct Session {
     int64_t ldx = 0;
     int *ord[2] = {nullptr, nullptr};
     double *ypay[2] = {nullptr, nullptr};  // y travelling with the row ids (L2 fits); null = gather path
+    const double *dw = nullptr;            // sample weights (four.py); dy is then y*w
+    double *wpay[2] = {nullptr, nullptr};  // the weights travelling like ypay
     int cur = 0;
     int64_t col_stride = 0;
     std::vector<HNode> nodes;

@@ -15,6 +15,7 @@ constexpr int EXACT_ROWS = 2048;         // nodes up to this size take the seque
 // the order arrays.
 struct SegDev {
     double total;   // sum of y over the node (approximate path); exact path recomputes it
+    double total_w; // weighted fits: sum of the weights of the node
     int start;
     int n;
     int pbase;      // first slot of this node's partial candidates
@@ -53,6 +54,7 @@ struct LevelArgs {
     int F_search;           // columns searched (local feature slice)
     const double *y;        // (N,) targets by row id (gather path)
     const double *ypay;     // [F_store][col_stride] y travelling with each row id (streaming path), or null
+    const double *wpay;     // weighted fits: the sample weights travelling the same way (ypay then holds y*w)
     const SegDev *segs;
     int n_segs;
 };
@@ -238,6 +240,11 @@ int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, i
                        int64_t col_stride, int F_store, int F_search, const PlanSeg *plan, const TileDesc *tiles,
                        int n_tiles, int64_t n_elems, const u32 *mask, u64 *status, u32 epoch, Partial *partials,
                        int variant);
+int launch_mul(b200dt_ctx *ctx, const double *a, const double *b, int64_t n, double *out);
+int launch_l2w_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles, int64_t n_elems,
+                    u64 *status, u32 epoch, Partial *partials);
+int launch_l2w_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small, int64_t n_elems,
+                     int total_col, double *ty, double *tw, Partial *partials);
 int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, double *ypay, int64_t col_stride,
                           int F_store, int64_t N);
 
@@ -249,9 +256,11 @@ int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, 
                     int64_t n_elems, int total_col, double *exact_total, Partial *partials, int variant);
 constexpr int FIN_SLICES_HOST = 64;  // == FIN_SLICES in l2.cu
 int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, int64_t max_records,
-                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out);
+                    Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out,
+                    bool flat_rule = false);
 int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, const int *marks /* [n][3]: f,start,k */,
                      int n_marks, int max_left, u32 *mask);
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
-                     u64 *status, u32 epoch, u32 *ticket, const double *y_in = nullptr, double *y_out = nullptr);
+                     u64 *status, u32 epoch, u32 *ticket, const double *y_in = nullptr, double *y_out = nullptr,
+                     const double *w_in = nullptr, double *w_out = nullptr);

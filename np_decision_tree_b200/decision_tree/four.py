@@ -45,19 +45,24 @@ class DecisionTree:
 
 
 def build_regression_tree(X, y, max_depth=2, min_improvement=1e-7, min_sample_leaf=1, weight=None):
-    """four.py:108-172.  ``weight`` (sample weights, four.py:116-117,21-30) is not on the GPU yet."""
-    if weight is not None:
-        raise NotImplementedError("sample weights (four.py:21-30) are not implemented on the GPU path yet")
+    """four.py:108-172.  ``weight``: optional (N,) sample weights (four.py:116-117, 21-30)."""
     tree = DecisionTree(2 ** (max_depth + 1))
     ctx = context_for(X, y)
     xp, xs, xk, N, F, ldx = matrix_arg(X)
     yp, ys, yk = _lib.as_arg(y, np.float64, "y")
     if xs != ys:
         raise ValueError("X and y must both be host arrays or both be CUDA tensors")
+    wp = None
+    if weight is not None:
+        wp, ws, wk = _lib.as_arg(weight, np.float64, "weight")
+        if ws != xs:
+            raise ValueError("weight must live where X and y live")
+        if int(np.prod(weight.shape)) != N:
+            raise ValueError("weight must have one entry per row")
     t = tree.tree_
     count = ctypes.c_int64(0)
     ctx.check(ctx.lib.b200dt_fit_ex(
-        ctx.handle, xp, yp, N, F, ldx, xs, _lib.L2, int(max_depth), float(min_improvement), int(min_sample_leaf), 1,
+        ctx.handle, xp, yp, wp, N, F, ldx, xs, _lib.L2, int(max_depth), float(min_improvement), int(min_sample_leaf), 1,
         _lib.NUMBER_BY_LEVEL | _lib.LEAF_IF_LE, t.children_left.ctypes.data, t.children_right.ctypes.data,
         t.feature.ctypes.data, t.threshold.ctypes.data, t.value.ctypes.data, t.n_node_samples.ctypes.data,
         t.feature.shape[0], ctypes.byref(count)))
