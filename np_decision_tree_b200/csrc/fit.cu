@@ -230,6 +230,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     s->cur = 0;
     u64 *k0 = nullptr, *k1 = nullptr;
     int64_t kcap = 0;
+    int payload_cols_done = 0;
     {
         const char *e = getenv("B200DT_FUSE");
         s->fuse_levels = e && e[0] == '1';
@@ -239,8 +240,11 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         kcap = (int64_t)F_store * s->col_stride;
         CKR(scratch_get(ctx, SB_YPAY0, (size_t)kcap * 8, (void **)&s->ypay[0]));
         CKR(scratch_get(ctx, SB_YPAY1, (size_t)kcap * 8, (void **)&s->ypay[1]));
-        k0 = (u64 *)s->ypay[0];
-        k1 = (u64 *)s->ypay[1];
+        // the sort borrows only the ALTERNATE payload buffer (two halves), so the primary one can be
+        // filled column batch by column batch while later batches are still in flight
+        kcap /= 2;
+        k0 = (u64 *)s->ypay[1];
+        k1 = (u64 *)s->ypay[1] + kcap;
     }
     // one sort per fit (one.py:139)
     if (n_h2d > 0) {
@@ -249,7 +253,11 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
             CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[b], 0));
             CKR(sort_columns_device(ctx, s->dX + c0, N, fb, s->ldx, s->ord[0] + c0 * s->col_stride,
                                     s->ord[1] + c0 * s->col_stride, s->col_stride, k0, k1, kcap));
+            if (s->ypay[0])   // y is on the device before the first batch: gather its payload now
+                CKR(launch_gather_payload(ctx, s->ord[0] + c0 * s->col_stride, s->dy,
+                                          s->ypay[0] + c0 * s->col_stride, s->col_stride, (int)fb, N));
         }
+        payload_cols_done = (int)F_local;
     } else {
         CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
     }
@@ -271,10 +279,13 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,
                                 s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
     }
-    if (s->ypay[0]) CKR(launch_gather_payload(ctx, s->ord[0], s->dy, s->ypay[0], s->col_stride, F_store, N));
+    if (s->ypay[0] && payload_cols_done < F_store)
+        CKR(launch_gather_payload(ctx, s->ord[0] + (int64_t)payload_cols_done * s->col_stride, s->dy,
+                                  s->ypay[0] + (int64_t)payload_cols_done * s->col_stride, s->col_stride,
+                                  F_store - payload_cols_done, N));
     if (s->dw) {
-        CKR(scratch_get(ctx, SB_WPAY0, (size_t)kcap * 8, (void **)&s->wpay[0]));
-        CKR(scratch_get(ctx, SB_WPAY1, (size_t)kcap * 8, (void **)&s->wpay[1]));
+        CKR(scratch_get(ctx, SB_WPAY0, (size_t)F_store * s->col_stride * 8, (void **)&s->wpay[0]));
+        CKR(scratch_get(ctx, SB_WPAY1, (size_t)F_store * s->col_stride * 8, (void **)&s->wpay[1]));
         CKR(launch_gather_payload(ctx, s->ord[0], s->dw, s->wpay[0], s->col_stride, F_store, N));
     }
     // (the look-back status arrays are sized per launch from the actual tile count)
