@@ -3,7 +3,8 @@
 This package restates, in numpy (+ one small C file for the running median),
 the algorithm of yupbank/np_decision_tree's hot path (decision_tree/one.py,
 decision_tree/strategy_l1.py, decision_tree/np_stream_median.pyx,
-decision_tree/utils.py).  Every function cites the reference file:line it
+decision_tree/utils.py, decision_tree/four.py, and the greedy classification search of
+decision_tree/strategy.py + decision_tree/tree_builder.py).  Every function cites the reference file:line it
 follows.  It is the checker the CUDA path is compared against.
 
 Who may import it: ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
@@ -35,4 +36,9 @@ from .np_tree_oracle import (  # noqa: F401
     LevelTreeArrays,
     l2_best_split_weighted,
     fit_l2_levelwise,
+    class_prefix_counts,
+    gini_surrogate,
+    p_at_1_surrogate,
+    class_split_node,
+    fit_classes,
 )

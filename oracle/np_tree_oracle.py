@@ -451,3 +451,111 @@ def fit_l2_levelwise(X, y, max_depth=2, min_improvement=1e-7, min_sample_leaf=1,
             rights.append((ro, node, False))
         level = lefts + rights
     return tree
+
+
+# --------------------------------------------------------------------------
+# classification: exhaustive gini / precision-at-1 search   
+# --------------------------------------------------------------------------
+def class_prefix_counts(sorted_labels, n_classes):
+    """(n, F, C) float64 running class counts down every sorted column.
+
+    ref: decision_tree/strategy.py:274-275 -- ``np.cumsum(y[orders], axis=0)`` on the
+    one-hot targets that tree_builder.py:157-158 builds with ``np.eye(max_classes)[y]``.
+    The counts are whole numbers, so the summation order cannot change them.
+    """
+    return np.cumsum(np.eye(n_classes)[sorted_labels], axis=0)
+
+
+def gini_surrogate(prefix):
+    """(n-1, F) score of every split position: sum_c L_c^2 / n_left + sum_c R_c^2 / n_right.
+
+    ref: decision_tree/strategy.py:32-55 (surrogate_gini_improvements called with two
+    arguments: candidates are rows [:-1], the node totals are row [-1]).
+    """
+    n = prefix.shape[0]
+    left, total = prefix[:-1], prefix[-1]
+    n_left = np.arange(1, n)[:, np.newaxis]
+    right = total - left
+    return (np.square(left).sum(axis=2) / n_left
+            + np.square(right).sum(axis=2) / (n - n_left))
+
+
+def p_at_1_surrogate(prefix):
+    """(n-1, F): largest class count on the left + largest class count on the right.
+
+    ref: decision_tree/strategy.py:79-100 (surrogate_p_at_k_improvements; its ``k`` is unused).
+    """
+    left, total = prefix[:-1], prefix[-1]
+    return np.max(left, axis=2) + np.max(total - left, axis=2)
+
+
+def class_split_node(X_node, onehot_node, criterion="gini", sort_kind=None):
+    """(column, threshold, improvement, split_row) of one node.
+
+    ref: decision_tree/strategy.py:272-283 (greedy_classification) and :313-323
+    (greedy_classification_p_at_k): per-node argsort, flat row-major argmax
+    (lowest position, then lowest column), threshold = the feature value at the
+    chosen position, improvement via surrogate_to_gini / surrogate_to_p_at_k
+    (strategy.py:103-108).
+    """
+    order = np.argsort(X_node, axis=0, kind=sort_kind)
+    labels = np.argmax(onehot_node, axis=1)
+    prefix = class_prefix_counts(labels[order], onehot_node.shape[1])
+    n = X_node.shape[0]
+    class_totals = onehot_node.sum(axis=0)
+    if criterion == "gini":
+        score = gini_surrogate(prefix)
+    elif criterion == "p_at_k":
+        score = p_at_1_surrogate(prefix)
+    else:
+        raise ValueError(criterion)
+    k, f = np.unravel_index(np.argmax(score), score.shape)
+    threshold = X_node[order[k, f], f]
+    if criterion == "gini":
+        improvement = score[k, f] / n - np.sum(np.square(class_totals / onehot_node.sum()))
+    else:
+        improvement = (score[k, f] - np.max(class_totals)) / n
+    return int(f), threshold, improvement, int(k)
+
+
+def fit_classes(X, labels, n_classes, max_depth=2, max_feature=100, min_improvement=0.01,
+                min_sample_leaf=1, criterion="gini", sort_kind=None):
+    """Depth-first classification tree with the reference's node order and leaf rules.
+
+    ref: decision_tree/tree_builder.py:56-96 (build_tree) as driven by
+    build_classification_tree (:149-159) with split_method=greedy_classification[_p_at_k];
+    decision_tree/base.py:13-21 (is_leaf: rows <= 2 * min_sample_leaf, or a single
+    distinct value in the one-hot block); tree_builder.py:24-41 (split_mask: rows go
+    left when value <= threshold, so equal values never straddle a split);
+    tree_builder.py:20-21 (leaf = first most frequent class).
+    Column sub-sampling (tree_builder.py:44-48, np.random) applies only when
+    F > max_feature and is not restated.
+    """
+    X = np.asarray(X)
+    labels = np.asarray(labels)
+    if X.shape[1] > max_feature:
+        raise NotImplementedError("random column sub-sampling (F > max_feature) is not restated")
+    onehot = np.eye(n_classes)[labels]
+    tree = TreeArrays(max_depth)
+    t = tree.tree_
+    pending = [(np.arange(X.shape[0]), -1, True, 0)]
+    while pending:
+        rows, parent, is_left, depth = pending.pop()
+        tree.max_node_ += 1
+        node = tree.max_node_
+        if parent >= 0:
+            (t.children_left if is_left else t.children_right)[parent] = node
+        Xn, yn = X[rows], onehot[rows]
+        leaf = rows.size <= 2 * min_sample_leaf or np.unique(yn).size <= 1 or depth >= max_depth
+        if not leaf:
+            f, threshold, improvement, _ = class_split_node(Xn, yn, criterion, sort_kind)
+            leaf = improvement < min_improvement
+        if leaf:
+            t.value[node] = np.argmax(yn.sum(axis=0))
+            continue
+        t.feature[node] = f
+        t.threshold[node] = threshold
+        goes_left = Xn[:, f] <= threshold
+        pending.append((rows[~goes_left], node, False, depth + 1))
+        pending.append((rows[goes_left], node, True, depth + 1))
+    return tree

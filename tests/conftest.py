@@ -26,6 +26,11 @@ def golden_configs():
 
 
 @pytest.fixture(scope="session")
+def golden_classes():
+    return np.load(os.path.join(GOLDEN, "reference_classes.npz"))
+
+
+@pytest.fixture(scope="session")
 def c2_data(golden_configs):
     """make_regression(10000, 100, random_state=0): BASELINE.json configs[0], configs[1]."""
     import hashlib

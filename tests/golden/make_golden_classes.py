@@ -1,0 +1,66 @@
+"""Generate tests/golden/reference_classes.npz by running the UNMODIFIED reference's
+classification builder (decision_tree/tree_builder.py + decision_tree/strategy.py).
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden_classes.py
+
+Feature values are continuous (distinct per column): the reference sorts each node with numpy's
+default unstable argsort, so only inputs without repeated feature values have a defined result.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from decision_tree import tree_builder, strategy, utils  # noqa: E402  (the reference)
+from make_golden import tree_dict  # noqa: E402
+
+
+def class_problem(seed, n, F, C, noise=0.5):
+    rs = np.random.RandomState(seed)
+    X = rs.standard_normal((n, F))
+    W = rs.standard_normal((F, C)) * (rs.uniform(size=(F, 1)) < 0.6)
+    labels = np.argmax(X @ W + noise * rs.standard_normal((n, C)), axis=1).astype(np.int64)
+    return X, labels
+
+
+METHODS = {"gini": strategy.greedy_classification, "p_at_k": strategy.greedy_classification_p_at_k}
+
+
+def main():
+    out = {}
+    cases = [("g0", "gini", 70, 300, 6, 3, 4, {}), ("g1", "gini", 71, 97, 4, 2, 6, {}),
+             ("g2", "gini", 72, 1000, 10, 10, 8, dict(min_improvement=1e-7)),
+             ("g3", "gini", 73, 513, 3, 23, 9, dict(min_improvement=1e-7)),
+             ("g4", "gini", 74, 5, 2, 2, 2, dict(min_improvement=0.0)),
+             ("g5", "gini", 75, 3000, 8, 5, 10, dict(min_improvement=1e-7)),
+             ("gk", "gini", 76, 400, 5, 4, 6, dict(min_improvement=0.02, min_sample_leaf=10)),
+             ("p0", "p_at_k", 80, 300, 6, 3, 4, {}), ("p1", "p_at_k", 81, 1000, 10, 10, 8, dict(min_improvement=1e-7)),
+             ("p2", "p_at_k", 82, 513, 3, 23, 9, dict(min_improvement=1e-7)),
+             ("pk", "p_at_k", 83, 400, 5, 4, 6, dict(min_improvement=0.02, min_sample_leaf=10))]
+    for name, crit, seed, n, F, C, depth, kw in cases:
+        X, labels = class_problem(seed, n, F, C)
+        t = tree_builder.build_classification_tree(X, labels, max_depth=depth, max_feature=F,
+                                                   split_method=METHODS[crit], max_classes=C, **kw)
+        out.update({f"cl_{name}_X": X, f"cl_{name}_labels": labels, f"cl_{name}_depth": np.int64(depth),
+                    f"cl_{name}_classes": np.int64(C), f"cl_{name}_criterion": np.array(crit),
+                    f"cl_{name}_min_improvement": np.float64(kw.get("min_improvement", 0.01)),
+                    f"cl_{name}_min_sample_leaf": np.int64(kw.get("min_sample_leaf", 1))})
+        out.update(tree_dict(f"cl_{name}_", t))
+        out[f"cl_{name}_pred"] = utils.inference(X, t)
+        # the root's single-node search (strategy.py:272-283 / :313-323)
+        col, thr, imp, _ = METHODS[crit](X, np.eye(C)[labels])
+        out[f"cl_{name}_root"] = np.array([col, thr, imp], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "reference_classes.npz"), **out)
+    print("reference_classes.npz", os.path.getsize(os.path.join(HERE, "reference_classes.npz")), "bytes",
+          {k[3:-9]: int(out[k]) + 1 for k in out if k.endswith("_max_node")})
+
+
+if __name__ == "__main__":
+    main()
