@@ -34,6 +34,8 @@ extern "C" {
 
 #define B200DT_L2 0 /* MSE: ref decision_tree/one.py                  */
 #define B200DT_L1 1 /* MAE: ref decision_tree/strategy_l1.py          */
+#define B200DT_GINI 2   /* gini:           ref decision_tree/strategy.py:32-55,272-283  */
+#define B200DT_P_AT_1 3 /* precision at 1: ref decision_tree/strategy.py:79-100,313-323 */
 
 typedef struct b200dt_ctx b200dt_ctx;
 
@@ -180,6 +182,28 @@ int b200dt_predict(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64
                    const int64_t *children_left, const int64_t *children_right,
                    const double *value, int64_t n_nodes, double *out_value, int32_t *out_leaf,
                    int out_space);
+
+/* ---- K6: classification trees (exhaustive gini / precision-at-1 search) -----------------
+ * replaces: tree_builder.build_classification_tree(X, y, max_depth, max_feature, min_improvement,
+ *           min_sample_leaf, split_method=greedy_classification[_p_at_k], max_classes)
+ *           ref tree_builder.py:56-96,149-159; strategy.py:272-283,313-323; base.py:13-21
+ * labels (N,) int32 in [0, n_classes), same memory space as X.  n_classes <= 256, N <= 2^26 and
+ * n_classes * 2^ceil(log2 N) <= 2^32 (class and row id share one 32-bit entry).  Pre-order node
+ * ids; a node is a leaf when rows <= 2 * min_sample_leaf, at max_depth, or when the best split's
+ * improvement < min_improvement; rows go left by VALUE (x <= threshold, tree_builder.py:31-34);
+ * leaf value = first most frequent class.  n_node_samples may be NULL.  Column sub-sampling
+ * (F > max_feature, np.random) is the caller's business: pass the columns to search. */
+int b200dt_fit_classes(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F,
+                       int64_t ldx, int space, int n_classes, int criterion, int max_depth,
+                       double min_improvement, int64_t min_sample_leaf, int64_t *children_left,
+                       int64_t *children_right, int64_t *feature, double *threshold, double *value,
+                       int32_t *n_node_samples, int64_t capacity, int64_t *node_count);
+/* One node: best (column, sorted position, threshold, surrogate score) over all columns with the
+ * reference's flat argmax (lowest position, then lowest column).
+ * replaces: strategy.greedy_classification / greedy_classification_p_at_k   ref strategy.py:272-283,313-323 */
+int b200dt_class_split_node(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t n, int64_t F,
+                            int64_t ldx, int space, int n_classes, int criterion, int64_t *out_f,
+                            int64_t *out_k, double *out_threshold, double *out_score);
 
 /* ---- measurement -------------------------------------------------------------------
  * When enabled, every kernel launch is bracketed by CUDA events on the launch stream;

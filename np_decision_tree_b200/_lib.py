@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200tree.so")
 
 HOST, DEVICE = 0, 1
-L2, L1 = 0, 1
+L2, L1, GINI, P_AT_1 = 0, 1, 2, 3
 NUMBER_BY_LEVEL, LEAF_IF_LE = 1, 2
 
 c_i64 = ctypes.c_int64
@@ -64,6 +64,11 @@ _SIGNATURES = {
     "b200dt_session_finish": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "b200dt_predict": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                c_i64, c_vp, c_vp, c_int]),
+    "b200dt_fit_classes": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_dbl, c_i64,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
+    "b200dt_class_split_node": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int,
+                                        ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl),
+                                        ctypes.POINTER(c_dbl)]),
     "b200dt_profile_enable": (c_int, [c_vp, c_int]),
     "b200dt_profile_reset": (c_int, [c_vp]),
     "b200dt_profile_count": (c_int, []),

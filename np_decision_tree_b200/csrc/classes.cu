@@ -1,0 +1,878 @@
+// K6: exhaustive multi-class split search (gini, precision-at-1) and the classification fit.
+//
+// replaces greedy_classification / greedy_classification_p_at_k   (ref decision_tree/strategy.py:272-283, 313-323)
+//          surrogate_gini_improvements / surrogate_p_at_k_improvements        (ref strategy.py:32-55, 79-100)
+//          build_classification_tree -> build_tree                          (ref tree_builder.py:56-96, 149-159)
+//
+// The reference re-sorts every node (`np.argsort(X[rows])`), gathers the one-hot targets into an
+// (n, F, C) array and cumsums it.  Here the columns are sorted ONCE; the class id of a row rides in
+// the bits above its row id inside the 32-bit order entry, so one 4-byte stream per (row, feature)
+// carries everything a level needs, and the stable partition (partition.cu, PAY == 3) keeps every
+// node's columns sorted -- for distinct feature values exactly the order the reference's per-node
+// argsort produces.
+//
+// All scanned quantities are whole numbers, so the search is EXACT (no summation-order issue):
+// with r_j = number of earlier same-class rows of sorted position j,
+//     sum_c L_c(k)^2        = sum_{j<=k} (2 r_j + 1)                              =: A(k)
+//     sum_c R_c(k)^2        = sum_c T_c^2 - 2 sum_{j<=k} T_{c_j} + A(k)           (R_c = T_c - L_c)
+//     max_c L_c(k)          = max_{j<=k} (r_j + 1)
+//     max_c R_c(k)          = max_{j>k} (T_{c_j} - r_j)
+// i.e. plain integer prefix sums / prefix maxima of per-row terms once r_j is known.  r_j needs the
+// per-class counts at the start of the tile: pass 1 writes per-tile class histograms, pass 2 turns
+// them into exclusive prefixes per (node, column), pass 3 re-reads the tile and scores it.
+// Algorithmic bytes: 2 x 4 per live (row, feature) per level (+ 4 + 1 + 4 for the partition).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include <math_constants.h>
+
+#include "session.cuh"
+
+constexpr int GT_ROWS = 32;
+constexpr int GT_TILE = 32 * GT_ROWS;  // sorted positions per warp tile
+
+struct CSeg {
+    long long st2;   // sum_c T_c^2 of the node
+    int start, n;
+    int tile_base;   // first tile of this node in the level's tile list
+    int ntiles;
+    int tmax;        // max_c T_c
+    int pad;
+};
+
+struct CPart {
+    double score;
+    int k;  // position inside the node; INT_MAX = no candidate in this tile
+    int pad;
+};
+
+struct CCand {
+    double score;      // best surrogate value of the node
+    double threshold;  // feature value at (k, f)
+    int k, f;
+    int k_ext;         // last position whose feature value equals the threshold (value-based split)
+    int pad;
+};
+
+constexpr int MAX_CLASS_CHUNKS_HOST = 8;  // n_classes <= 256
+
+namespace {
+
+__device__ __forceinline__ u32 ld_stream_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// orders[f][p] |= label[row] << row_bits
+__global__ void __launch_bounds__(256) pack_labels_kernel(u32 *orders, int64_t col_stride, int F, int64_t N,
+                                                          const int *__restrict__ labels, int row_bits) {
+    const int f = blockIdx.y;
+    u32 *col = orders + (int64_t)f * col_stride;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < N; p += (int64_t)gridDim.x * 256) {
+        const u32 row = col[p];
+        col[p] = row | ((u32)__ldg(labels + row) << row_bits);
+    }
+}
+
+__global__ void __launch_bounds__(256) label_check_hist_kernel(const int *__restrict__ labels, int64_t N, int C,
+                                                               unsigned long long *hist, int *bad) {
+    __shared__ int sh[32 * MAX_CLASS_CHUNKS_HOST];
+    const u32 lt = lanemask_lt();
+    for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0;
+    __syncthreads();
+    const int64_t n_round = (N + 255) / 256 * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * 256) {
+        int c = i < N ? labels[i] : -1;
+        if (i < N && (c < 0 || c >= C)) {
+            *bad = 1;
+            c = -1;
+        }
+        const u32 peers = __match_any_sync(FULL_MASK, c);
+        if (c >= 0 && (peers & lt) == 0) atomicAdd(&sh[c], __popc(peers));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256)
+        if (sh[c]) atomicAdd(hist + c, (unsigned long long)sh[c]);
+}
+
+// ---- pass 1: class histogram of every (tile, column) ------------------------------------
+__global__ void __launch_bounds__(256) class_hist_kernel(const u32 *__restrict__ orders, int64_t col_stride,
+                                                         const CSeg *__restrict__ segs,
+                                                         const TileDesc *__restrict__ tiles, int n_tiles, int F,
+                                                         int C, int row_bits, int *__restrict__ hist) {
+    extern __shared__ int sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    int *h = sm + warp * (C + 1);
+    const int64_t total = (int64_t)n_tiles * F;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total; t += (int64_t)gridDim.x * 8) {
+        const int f = (int)(t % F), ti = (int)(t / F);
+        const TileDesc td = tiles[ti];
+        const CSeg sg = segs[td.seg];
+        const int off = td.tin * GT_TILE;
+        const int cnt = min(GT_TILE, sg.n - off);
+        const u32 *col = orders + (int64_t)f * col_stride + sg.start + off;
+        u32 v[GT_ROWS];
+#pragma unroll
+        for (int i = 0; i < GT_ROWS; ++i) v[i] = (i * 32 + lane < cnt) ? ld_stream_u32(col + i * 32 + lane) : 0u;
+        for (int c = lane; c <= C; c += 32) h[c] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < GT_ROWS; ++i) {
+            const int c = (i * 32 + lane < cnt) ? (int)(v[i] >> row_bits) : C;  // slot C absorbs the padding
+            const u32 peers = __match_any_sync(FULL_MASK, c);
+            if ((peers & lt) == 0) h[c] += __popc(peers);  // one writer per class
+            __syncwarp();
+        }
+        int *out = hist + ((int64_t)f * n_tiles + ti) * C;
+        for (int c = lane; c < C; c += 32) out[c] = h[c];
+        __syncwarp();
+    }
+}
+
+// ---- pass 2: exclusive prefix of the histograms along the tiles of each (node, column) -----
+// one warp per (node, column), lanes = classes.  Also the largest right-hand class count at
+// the end of every tile (precision-at-1 needs it as the seed of its backward pass).
+constexpr int MAX_CLASS_CHUNKS = MAX_CLASS_CHUNKS_HOST;
+
+__global__ void __launch_bounds__(256) class_scan_kernel(const CSeg *__restrict__ segs, int n_segs, int F, int C,
+                                                         int n_tiles, const int *__restrict__ tot,
+                                                         const int *__restrict__ hist, int *__restrict__ excl,
+                                                         int *__restrict__ rmax_end) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_work = (int64_t)n_segs * F;
+    const int nch = (C + 31) / 32;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work;
+         w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int seg = (int)(w / F), f = (int)(w % F);
+        const CSeg sg = segs[seg];
+        int run[MAX_CLASS_CHUNKS], T[MAX_CLASS_CHUNKS];
+#pragma unroll
+        for (int ch = 0; ch < MAX_CLASS_CHUNKS; ++ch) {
+            run[ch] = 0;
+            const int c = ch * 32 + lane;
+            T[ch] = (ch < nch && c < C) ? tot[(int64_t)seg * C + c] : 0;
+        }
+        const int64_t base = ((int64_t)f * n_tiles + sg.tile_base) * C;
+#pragma unroll 4
+        for (int t = 0; t < sg.ntiles; ++t) {
+            int rm = 0;
+#pragma unroll
+            for (int ch = 0; ch < MAX_CLASS_CHUNKS; ++ch) {
+                const int c = ch * 32 + lane;
+                if (ch < nch && c < C) {
+                    const int64_t idx = base + (int64_t)t * C + c;
+                    const int hv = hist[idx];
+                    excl[idx] = run[ch];
+                    run[ch] += hv;
+                    rm = max(rm, T[ch] - run[ch]);
+                }
+            }
+            if (rmax_end) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) rm = max(rm, __shfl_xor_sync(FULL_MASK, rm, m));
+                if (lane == 0) rmax_end[(int64_t)f * n_tiles + sg.tile_base + t] = rm;
+            }
+        }
+    }
+}
+
+// ---- pass 3: score every split position of the tile, keep the best ------------------------
+// CRIT 0: gini surrogate (strategy.py:32-55); CRIT 1: precision-at-1 surrogate (strategy.py:79-100)
+template <int CRIT>
+__global__ void __launch_bounds__(256) class_score_kernel(const u32 *__restrict__ orders, int64_t col_stride,
+                                                          const CSeg *__restrict__ segs,
+                                                          const TileDesc *__restrict__ tiles, int n_tiles, int F,
+                                                          int C, int row_bits, const int *__restrict__ excl,
+                                                          const int *__restrict__ tot,
+                                                          const int *__restrict__ rmax_end,
+                                                          CPart *__restrict__ partials) {
+    extern __shared__ int sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    const int per_warp = 2 * (C + 1) + (CRIT == 1 ? 2 * GT_TILE : 0);
+    int *cnt = sm + warp * per_warp;  // running class counts (slot C: padding lanes)
+    int *T = cnt + (C + 1);           // class totals of the node
+    int *s_ml = T + (C + 1);          // CRIT 1: max_c L_c at each position
+    int *s_sr = s_ml + GT_TILE;       // CRIT 1: T_c - r of each position
+    const int64_t total = (int64_t)n_tiles * F;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total; t += (int64_t)gridDim.x * 8) {
+        const int f = (int)(t % F), ti = (int)(t / F);
+        const TileDesc td = tiles[ti];
+        const CSeg sg = segs[td.seg];
+        const int off = td.tin * GT_TILE;
+        const int n = sg.n;
+        const int cnt_here = min(GT_TILE, n - off);
+        const u32 *col = orders + (int64_t)f * col_stride + sg.start + off;
+        u32 v[GT_ROWS];
+#pragma unroll
+        for (int i = 0; i < GT_ROWS; ++i) v[i] = (i * 32 + lane < cnt_here) ? ld_stream_u32(col + i * 32 + lane) : 0u;
+        const int *ex = excl + ((int64_t)f * n_tiles + ti) * C;
+        long long a0 = 0, b0 = 0;
+        int m0 = 0;
+        for (int c = lane; c < C; c += 32) {
+            const int e = ex[c], tc = tot[(int64_t)td.seg * C + c];
+            cnt[c] = e;
+            T[c] = tc;
+            a0 += (long long)e * e;
+            b0 += (long long)tc * e;
+            m0 = max(m0, e);
+        }
+        if (lane == 0) {
+            cnt[C] = 0;
+            T[C] = 0;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            a0 += __shfl_xor_sync(FULL_MASK, a0, m);
+            b0 += __shfl_xor_sync(FULL_MASK, b0, m);
+            m0 = max(m0, __shfl_xor_sync(FULL_MASK, m0, m));
+        }
+        __syncwarp();
+        double best = -CUDART_INF;
+        int best_k = 0x7fffffff;
+        long long a_run = a0, b_run = b0;
+        int ml_run = m0;
+#pragma unroll
+        for (int i = 0; i < GT_ROWS; ++i) {
+            const int e = i * 32 + lane;
+            const bool ok = e < cnt_here;
+            const int c = ok ? (int)(v[i] >> row_bits) : C;
+            const u32 peers = __match_any_sync(FULL_MASK, c);
+            const int r = cnt[c] + __popc(peers & lt);  // earlier rows of the same class in this node
+            __syncwarp();
+            if ((peers & lt) == 0) cnt[c] += __popc(peers);
+            __syncwarp();
+            const int kk = off + e;
+            if (CRIT == 0) {
+                u32 a = ok ? 2u * (u32)r + 1u : 0u, b = ok ? (u32)T[c] : 0u;  // row sums stay below 2^32 (N <= 2^26)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 ua = __shfl_up_sync(FULL_MASK, a, d), ub = __shfl_up_sync(FULL_MASK, b, d);
+                    if (lane >= d) {
+                        a += ua;
+                        b += ub;
+                    }
+                }
+                if (ok && kk < n - 1) {
+                    const long long SL = a_run + (long long)a;
+                    const long long SR = sg.st2 - 2 * (b_run + (long long)b) + SL;
+                    // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
+                    const double sc = __dadd_rn(__ddiv_rn((double)SL, (double)(kk + 1)),
+                                                __ddiv_rn((double)SR, (double)(n - kk - 1)));
+                    if (sc > best) {
+                        best = sc;
+                        best_k = kk;
+                    }
+                }
+                a_run += (long long)__shfl_sync(FULL_MASK, a, 31);
+                b_run += (long long)__shfl_sync(FULL_MASK, b, 31);
+            } else {
+                int ml = ok ? r + 1 : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, ml, d);
+                    if (lane >= d) ml = max(ml, u);
+                }
+                ml = max(ml, ml_run);
+                s_ml[e] = ml;
+                s_sr[e] = ok ? T[c] - r : 0;
+                ml_run = __shfl_sync(FULL_MASK, ml, 31);
+            }
+        }
+        if (CRIT == 1) {
+            __syncwarp();
+            int mr_run = rmax_end[(int64_t)f * n_tiles + ti];  // largest class count right of this tile
+#pragma unroll 4
+            for (int i = GT_ROWS - 1; i >= 0; --i) {
+                const int e = i * 32 + lane;
+                int sfx = s_sr[e];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_down_sync(FULL_MASK, sfx, d);
+                    if (lane + d < 32) sfx = max(sfx, u);
+                }
+                int after = __shfl_down_sync(FULL_MASK, sfx, 1);  // max over the later lanes of this row
+                if (lane == 31) after = 0;
+                const int mr = max(mr_run, after);
+                const int kk = off + e;
+                if (e < cnt_here && kk < n - 1) {
+                    const double sc = (double)(s_ml[e] + mr);  // strategy.py:97-100
+                    if (sc >= best) {  // positions are visited in decreasing order: ties go to the lower one
+                        best = sc;
+                        best_k = kk;
+                    }
+                }
+                mr_run = max(mr_run, __shfl_sync(FULL_MASK, sfx, 0));
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ob = shfl_xor_d(best, m);
+            const int ok2 = __shfl_xor_sync(FULL_MASK, best_k, m);
+            if (ob > best || (ob == best && ok2 < best_k)) {
+                best = ob;
+                best_k = ok2;
+            }
+        }
+        if (lane == 0) {
+            CPart p;
+            p.score = best;
+            p.k = best_k;
+            p.pad = 0;
+            partials[(int64_t)f * n_tiles + ti] = p;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- per-node arg-best over (tile, column): flat row-major rule (position, then column) -----
+// strategy.py:277-278: np.unravel_index(np.argmax(improvements), shape) on an (n-1, F) array
+__global__ void __launch_bounds__(256) class_finalize_kernel(const CSeg *__restrict__ segs, int F, int n_tiles,
+                                                             const CPart *__restrict__ partials,
+                                                             const u32 *__restrict__ orders, int64_t col_stride,
+                                                             int row_mask, const double *__restrict__ X, int64_t ldx,
+                                                             CCand *__restrict__ out) {
+    __shared__ double s_score[256];
+    __shared__ int s_k[256], s_f[256];
+    const CSeg sg = segs[blockIdx.x];
+    double best = -CUDART_INF;
+    int bk = 0x7fffffff, bf = 0x7fffffff;
+    const int64_t n_rec = (int64_t)sg.ntiles * F;
+    for (int64_t r = threadIdx.x; r < n_rec; r += 256) {
+        const int f = (int)(r / sg.ntiles), tt = (int)(r % sg.ntiles);
+        const CPart p = partials[(int64_t)f * n_tiles + sg.tile_base + tt];
+        if (p.k == 0x7fffffff) continue;
+        if (p.score > best || (p.score == best && (p.k < bk || (p.k == bk && f < bf)))) {
+            best = p.score;
+            bk = p.k;
+            bf = f;
+        }
+    }
+    s_score[threadIdx.x] = best;
+    s_k[threadIdx.x] = bk;
+    s_f[threadIdx.x] = bf;
+    __syncthreads();
+    for (int m = 128; m >= 1; m >>= 1) {
+        if ((int)threadIdx.x < m) {
+            const double os = s_score[threadIdx.x + m];
+            const int ok = s_k[threadIdx.x + m], of = s_f[threadIdx.x + m];
+            const double ms = s_score[threadIdx.x];
+            const int mk = s_k[threadIdx.x], mf = s_f[threadIdx.x];
+            if (ok != 0x7fffffff && (mk == 0x7fffffff || os > ms || (os == ms && (ok < mk || (ok == mk && of < mf))))) {
+                s_score[threadIdx.x] = os;
+                s_k[threadIdx.x] = ok;
+                s_f[threadIdx.x] = of;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        CCand c;
+        c.score = s_score[0];
+        c.k = s_k[0];
+        c.f = s_f[0];
+        c.k_ext = c.k;
+        c.threshold = 0.0;
+        c.pad = 0;
+        if (c.k != 0x7fffffff) {
+            const u32 *col = orders + (int64_t)c.f * col_stride + sg.start;
+            const double thr = X[(int64_t)(col[c.k] & (u32)row_mask) * ldx + c.f];  // strategy.py:279-280
+            // tree_builder.py:31-34 splits by value (<= threshold): equal values right of k go left too
+            int lo = c.k, hi = sg.n - 1;
+            while (lo < hi) {
+                const int mid = lo + (hi - lo + 1) / 2;
+                if (X[(int64_t)(col[mid] & (u32)row_mask) * ldx + c.f] <= thr)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            c.threshold = thr;
+            c.k_ext = lo;
+        } else {
+            c.k = -1;
+        }
+        out[blockIdx.x] = c;
+    }
+}
+
+// left rows of every split node: side-mask bits + their class counts
+__global__ void __launch_bounds__(256) class_mark_kernel(const u32 *__restrict__ orders, int64_t col_stride,
+                                                         const int *__restrict__ marks, int C, int row_bits,
+                                                         u32 *mask, int *lcount) {
+    extern __shared__ int sh[];
+    const int m = blockIdx.y;
+    const int f = marks[3 * m], start = marks[3 * m + 1], k = marks[3 * m + 2];
+    for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0;
+    __syncthreads();
+    const u32 *col = orders + (int64_t)f * col_stride + start;
+    const u32 rmask = (1u << row_bits) - 1u;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j <= k; j += gridDim.x * 256) {
+        const u32 v = col[j];
+        const u32 row = v & rmask;
+        atomicOr(&mask[row >> 5], 1u << (row & 31));
+        atomicAdd(&sh[v >> row_bits], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256)
+        if (sh[c]) atomicAdd(&lcount[(int64_t)m * C + c], sh[c]);
+}
+
+// numpy's pairwise float64 summation (np.sum of a contiguous 1-D array), for the host-side
+// improvement test: surrogate_to_gini sums C squared class fractions (strategy.py:107-108)
+double np_pairwise_sum(const double *a, int64_t n) {
+    if (n < 8) {
+        double r = -0.0;
+        for (int64_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int64_t i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+struct CNode {
+    int parent = -1, is_left = 1, depth = 0, start = 0, n = 0;
+    int feature = -2, left = -1, right = -1;
+    double thr = -2.0, value = 0.0;
+    bool leaf = false;
+};
+
+template <typename T>
+int upload_vec(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const std::vector<T> &src, T *dst) {
+    if (src.empty()) return 0;
+    void *stage;
+    CKR(pinned_get(ctx, pin_slot, pin_off + src.size() * sizeof(T), &stage));
+    memcpy((char *)stage + pin_off, src.data(), src.size() * sizeof(T));
+    CK(cudaMemcpyAsync(dst, (char *)stage + pin_off, src.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int resident_grid(b200dt_ctx *ctx, const void *kern, size_t smem, int64_t work_warps) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)per_sm * ctx->sm_count;
+    const int64_t need = (work_warps + 7) / 8;
+    if (grid > need) grid = need;
+    return (int)std::max<int64_t>(grid, 1);
+}
+
+}  // namespace
+
+// Grows the tree (or, with single_node_out set, only searches the root).
+static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F, int64_t ldx,
+                          int space, int C, int criterion, int max_depth, double min_improvement,
+                          int64_t min_sample_leaf, int64_t *children_left, int64_t *children_right,
+                          int64_t *feature, double *threshold, double *value, int32_t *n_node_samples,
+                          int64_t capacity, int64_t *node_count, CCand *single_node_out) {
+    if (N <= 0 || F <= 0) return ctx->fail_msg("fit_classes: empty input");
+    if (criterion != B200DT_GINI && criterion != B200DT_P_AT_1) return ctx->fail_msg("fit_classes: unknown criterion");
+    if (C < 1 || C > 32 * MAX_CLASS_CHUNKS) return ctx->fail_msg("fit_classes: n_classes must be in [1, 256]");
+    if (N > (1ll << 26)) return ctx->fail_msg("fit_classes: N must be <= 2^26 (exact integer class statistics)");
+    if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit_classes: max_depth out of range [0, 30]");
+    int row_bits = 1;
+    while ((1ll << row_bits) < N) ++row_bits;
+    if ((int64_t)C > (1ll << (32 - row_bits)))
+        return ctx->fail_msg("fit_classes: n_classes * N does not fit the packed 32-bit (class, row) entries");
+    const int row_mask = (int)((1u << row_bits) - 1u);
+    const int64_t stride = (N + 31) / 32 * 32;
+
+    // inputs on the device
+    const double *dX = X;
+    const int *dlab = labels;
+    int64_t dld = ldx;
+    if (space == B200DT_HOST) {
+        double *bx;
+        int *bl;
+        CKR(scratch_get(ctx, SB_X, (size_t)N * F * 8, (void **)&bx));
+        CKR(scratch_get(ctx, SB_Y, (size_t)N * 8, (void **)&bl));
+        CK(cudaMemcpy2DAsync(bx, (size_t)F * 8, X, (size_t)ldx * 8, (size_t)F * 8, (size_t)N, cudaMemcpyHostToDevice,
+                             ctx->stream));
+        CK(cudaMemcpyAsync(bl, labels, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+        dX = bx;
+        dlab = bl;
+        dld = F;
+    }
+    // root class totals (+ label range check)
+    unsigned long long *d_roothist;
+    CKR(scratch_get(ctx, SB_MISC, (size_t)C * 8 + 64, (void **)&d_roothist));
+    CK(cudaMemsetAsync(d_roothist, 0, (size_t)C * 8 + 64, ctx->stream));
+    {
+        LaunchScope ls(ctx, KC_MISC, 4.0 * (double)N);
+        label_check_hist_kernel<<<(unsigned)std::min<int64_t>(1024, (N + 255) / 256), 256, 0, ctx->stream>>>(
+            dlab, N, C, d_roothist, (int *)(d_roothist + C));
+    }
+    CK(cudaGetLastError());
+    std::vector<unsigned long long> h_root(C + 1);
+    CK(cudaMemcpyAsync(h_root.data(), d_roothist, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((int)h_root[C] != 0) return ctx->fail_msg("fit_classes: labels must be integers in [0, n_classes)");
+
+    // one sort per fit; the class id then joins the row id
+    int *ord[2];
+    CKR(scratch_get(ctx, SB_ORD_A, (size_t)F * stride * 4, (void **)&ord[0]));
+    CKR(scratch_get(ctx, SB_ORD_B, (size_t)F * stride * 4, (void **)&ord[1]));
+    CKR(sort_columns_device(ctx, dX, N, F, dld, ord[0], ord[1], stride));
+    {
+        LaunchScope ls(ctx, KC_PAYLOAD, 12.0 * (double)N * F);
+        pack_labels_kernel<<<dim3((unsigned)std::min<int64_t>(2048, (N + 255) / 256), (unsigned)F), 256, 0, ctx->stream>>>(
+            (u32 *)ord[0], stride, (int)F, N, dlab, row_bits);
+    }
+    CK(cudaGetLastError());
+    int cur = 0;
+    u32 *d_mask;
+    CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&d_mask));
+
+    std::vector<CNode> nodes(1);
+    std::vector<long long> counts(C);  // counts[node * C + c]
+    for (int c = 0; c < C; ++c) counts[c] = (long long)h_root[c];
+    nodes[0].n = (int)N;
+    auto leaf_by_size = [&](const CNode &nd) {
+        // base.py:13-21 (rows <= 2 * min_sample_leaf; a one-hot block with a single distinct value: no rows,
+        // or a single class column) and tree_builder.py:74 (depth limit)
+        return (int64_t)nd.n <= 2 * min_sample_leaf || nd.n == 0 || C == 1 || nd.depth >= max_depth;
+    };
+    auto first_argmax = [&](int node) {  // tree_builder.py:20-21: np.argmax of the class counts
+        int best = 0;
+        for (int c = 1; c < C; ++c)
+            if (counts[(size_t)node * C + c] > counts[(size_t)node * C + best]) best = c;
+        return (double)best;
+    };
+    std::vector<int> live;
+    if (single_node_out == nullptr && leaf_by_size(nodes[0])) {
+        nodes[0].leaf = true;
+        nodes[0].value = first_argmax(0);
+    } else {
+        live.push_back(0);
+    }
+
+    std::vector<CSeg> segs;
+    std::vector<TileDesc> tiles;
+    std::vector<int> tot, marks;
+    std::vector<SegDev> psegs;
+    std::vector<TileDesc> ptiles;
+    std::vector<double> frac(C);
+    while (!live.empty()) {
+        const int n_live = (int)live.size();
+        segs.resize(n_live);
+        tiles.clear();
+        tot.resize((size_t)n_live * C);
+        int64_t elems = 0;
+        for (int i = 0; i < n_live; ++i) {
+            const CNode &nd = nodes[live[i]];
+            if (nd.n < 2)
+                return ctx->fail_msg("fit_classes: attempt to split a node with a single row (min_sample_leaf < 1); "
+                                     "the reference raises ValueError here (argmax of an empty sequence)");
+            CSeg sg;
+            sg.start = nd.start;
+            sg.n = nd.n;
+            sg.tile_base = (int)tiles.size();
+            sg.ntiles = (nd.n + GT_TILE - 1) / GT_TILE;
+            sg.st2 = 0;
+            sg.tmax = 0;
+            sg.pad = 0;
+            for (int c = 0; c < C; ++c) {
+                const long long tc = counts[(size_t)live[i] * C + c];
+                tot[(size_t)i * C + c] = (int)tc;
+                sg.st2 += tc * tc;
+                sg.tmax = std::max(sg.tmax, (int)tc);
+            }
+            segs[i] = sg;
+            for (int t = 0; t < sg.ntiles; ++t) tiles.push_back(TileDesc{i, t});
+            elems += nd.n;
+        }
+        const int n_tiles = (int)tiles.size();
+        CSeg *d_segs;
+        TileDesc *d_tiles;
+        int *d_tot, *d_hist, *d_excl, *d_rmax;
+        CPart *d_part;
+        CCand *d_cand;
+        const size_t hist_elems = (size_t)n_tiles * F * C;
+        CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(CSeg) + 64, (void **)&d_segs));
+        CKR(scratch_get(ctx, SB_TILES, (size_t)n_tiles * sizeof(TileDesc) + 64, (void **)&d_tiles));
+        CKR(scratch_get(ctx, SB_TMP2, (size_t)n_live * C * 4 + 64, (void **)&d_tot));
+        CKR(scratch_get(ctx, SB_L1_A, hist_elems * 4 + 64, (void **)&d_hist));
+        CKR(scratch_get(ctx, SB_L1_B, hist_elems * 4 + 64, (void **)&d_excl));
+        CKR(scratch_get(ctx, SB_L1_C, (size_t)n_tiles * F * 4 + 64, (void **)&d_rmax));
+        CKR(scratch_get(ctx, SB_PARTIAL, (size_t)n_tiles * F * sizeof(CPart) + 64, (void **)&d_part));
+        CKR(scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(CCand) + 64, (void **)&d_cand));
+        size_t po = 0;
+        CKR(upload_vec(ctx, PIN_CLASS, po, segs, d_segs));
+        po += segs.size() * sizeof(CSeg) + 64;
+        CKR(upload_vec(ctx, PIN_CLASS, po, tiles, d_tiles));
+        po += tiles.size() * sizeof(TileDesc) + 64;
+        CKR(upload_vec(ctx, PIN_CLASS, po, tot, d_tot));
+        po += tot.size() * 4 + 64;
+
+        const u32 *d_ord = (const u32 *)ord[cur];
+        const int64_t work = (int64_t)n_tiles * F;
+        {
+            const size_t smem = (size_t)8 * (C + 1) * 4;
+            const int grid = resident_grid(ctx, (const void *)class_hist_kernel, smem, work);
+            LaunchScope ls(ctx, KC_CLASS_HIST, 4.0 * (double)elems * F);
+            class_hist_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
+                                                                row_bits, d_hist);
+        }
+        CK(cudaGetLastError());
+        {
+            const int64_t warps = (int64_t)n_live * F;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16));
+            LaunchScope ls(ctx, KC_MISC, 8.0 * (double)hist_elems);
+            class_scan_kernel<<<grid, 256, 0, ctx->stream>>>(d_segs, n_live, (int)F, C, n_tiles, d_tot, d_hist, d_excl,
+                                                             criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
+        }
+        CK(cudaGetLastError());
+        {
+            const bool patk = criterion == B200DT_P_AT_1;
+            const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;
+            const void *kern = patk ? (const void *)class_score_kernel<1> : (const void *)class_score_kernel<0>;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = resident_grid(ctx, kern, smem, work);
+            LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
+            if (patk)
+                class_score_kernel<1><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
+                                                                        row_bits, d_excl, d_tot, d_rmax, d_part);
+            else
+                class_score_kernel<0><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
+                                                                        row_bits, d_excl, d_tot, d_rmax, d_part);
+        }
+        CK(cudaGetLastError());
+        {
+            LaunchScope ls(ctx, KC_FINALIZE, (double)work * sizeof(CPart));
+            class_finalize_kernel<<<n_live, 256, 0, ctx->stream>>>(d_segs, (int)F, n_tiles, d_part, d_ord, stride, row_mask,
+                                                                   dX, dld, d_cand);
+        }
+        CK(cudaGetLastError());
+        CCand *h_cand;
+        CKR(pinned_get(ctx, PIN_RESULT, (size_t)n_live * sizeof(CCand), (void **)&h_cand));
+        CK(cudaMemcpyAsync(h_cand, d_cand, (size_t)n_live * sizeof(CCand), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (single_node_out) {
+            *single_node_out = h_cand[0];
+            return 0;
+        }
+
+        // leaf or split (tree_builder.py:83-94)
+        marks.clear();
+        std::vector<int> split_nodes;
+        int max_left = 0;
+        for (int i = 0; i < n_live; ++i) {
+            const int nid = live[i];
+            const CCand &w = h_cand[i];
+            if (w.k < 0) return ctx->fail_msg("fit_classes: a node produced no split candidate");
+            const double nn = (double)nodes[nid].n;
+            double improvement;
+            if (criterion == B200DT_GINI) {
+                for (int c = 0; c < C; ++c) {
+                    const double fr = (double)counts[(size_t)nid * C + c] / nn;
+                    frac[c] = fr * fr;
+                }
+                improvement = w.score / nn - np_pairwise_sum(frac.data(), C);  // strategy.py:107-108
+            } else {
+                improvement = (w.score - (double)segs[i].tmax) / nn;           // strategy.py:103-104
+            }
+            if (improvement < min_improvement) {
+                nodes[nid].leaf = true;
+                nodes[nid].value = first_argmax(nid);
+                continue;
+            }
+            nodes[nid].feature = w.f;
+            nodes[nid].thr = w.threshold;
+            split_nodes.push_back(i);
+            marks.push_back(w.f);
+            marks.push_back(nodes[nid].start);
+            marks.push_back(w.k_ext);
+            max_left = std::max(max_left, w.k_ext + 1);
+        }
+        if (split_nodes.empty()) break;
+        const int n_split = (int)split_nodes.size();
+        int *d_marks, *d_lcount;
+        CKR(scratch_get(ctx, SB_TMP_I64, (size_t)n_split * 12 + 64, (void **)&d_marks));
+        CKR(scratch_get(ctx, SB_L1_D, (size_t)n_split * C * 4 + 64, (void **)&d_lcount));
+        CKR(upload_vec(ctx, PIN_CLASS, po, marks, d_marks));
+        po += marks.size() * 4 + 64;
+        CK(cudaMemsetAsync(d_mask, 0, (size_t)((N + 31) / 32) * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_lcount, 0, (size_t)n_split * C * 4, ctx->stream));
+        {
+            int gx = std::max(1, std::min(2048, (max_left + 255) / 256));
+            for (int m0 = 0; m0 < n_split; m0 += 65535) {
+                const int nm = std::min(65535, n_split - m0);
+                LaunchScope ls(ctx, KC_MARK, 0.0);
+                class_mark_kernel<<<dim3(gx, nm), 256, (size_t)C * 4, ctx->stream>>>(d_ord, stride, d_marks + 3 * m0, C,
+                                                                                   row_bits, d_mask,
+                                                                                   d_lcount + (size_t)m0 * C);
+            }
+        }
+        CK(cudaGetLastError());
+        int *h_lcount;
+        CKR(pinned_get(ctx, PIN_MISC, (size_t)n_split * C * 4, (void **)&h_lcount));
+        CK(cudaMemcpyAsync(h_lcount, d_lcount, (size_t)n_split * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+
+        std::vector<int> next_live;
+        psegs.clear();
+        ptiles.clear();
+        int64_t pelems = 0;
+        for (int j = 0; j < n_split; ++j) {
+            const int i = split_nodes[j], nid = live[i];
+            const int start = nodes[nid].start, n = nodes[nid].n, nl = h_cand[i].k_ext + 1;
+            const int depth = nodes[nid].depth;
+            int child[2];
+            for (int side = 0; side < 2; ++side) {
+                CNode ch;
+                ch.parent = nid;
+                ch.is_left = side == 0;
+                ch.depth = depth + 1;
+                ch.start = side == 0 ? start : start + nl;
+                ch.n = side == 0 ? nl : n - nl;
+                nodes.push_back(ch);
+                child[side] = (int)nodes.size() - 1;
+                counts.resize(nodes.size() * (size_t)C);
+                for (int c = 0; c < C; ++c) {
+                    const long long lc = h_lcount[(size_t)j * C + c];
+                    counts[(size_t)child[side] * C + c] = side == 0 ? lc : counts[(size_t)nid * C + c] - lc;
+                }
+            }
+            nodes[nid].left = child[0];
+            nodes[nid].right = child[1];
+            bool any_search = false;
+            for (int side = 0; side < 2; ++side) {
+                CNode &ch = nodes[child[side]];
+                if (leaf_by_size(ch)) {
+                    ch.leaf = true;
+                    ch.value = first_argmax(child[side]);
+                } else {
+                    next_live.push_back(child[side]);
+                    any_search = true;
+                }
+            }
+            if (any_search) {
+                SegDev sg;
+                sg.total = sg.total_w = 0.0;
+                sg.start = start;
+                sg.n = n;
+                sg.pbase = 0;
+                sg.np = (n + PT_TILE - 1) / PT_TILE;
+                sg.nleft = nl;
+                sg.exact = 0;
+                sg.pstep = 1;
+                sg.pside = 0;
+                const int si = (int)psegs.size();
+                psegs.push_back(sg);
+                for (int t = 0; t < sg.np; ++t) ptiles.push_back(TileDesc{si, t});
+                pelems += n;
+            }
+        }
+        if (!psegs.empty()) {
+            SegDev *d_psegs;
+            TileDesc *d_ptiles;
+            u64 *pstatus;
+            CKR(scratch_get(ctx, SB_PLAN, psegs.size() * sizeof(SegDev) + 64, (void **)&d_psegs));
+            CKR(scratch_get(ctx, SB_TILES, ptiles.size() * sizeof(TileDesc) + 64, (void **)&d_ptiles));
+            CKR(upload_vec(ctx, PIN_CLASS, po, psegs, d_psegs));
+            po += psegs.size() * sizeof(SegDev) + 64;
+            CKR(upload_vec(ctx, PIN_CLASS, po, ptiles, d_ptiles));
+            CKR(scratch_get(ctx, SB_STATUS_P, (ptiles.size() * (size_t)F + 1) * 8, (void **)&pstatus, true));
+            if (ctx->epoch >= (1u << 30) - 2) {
+                for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_VAL2, SB_STATUS_P, SB_L1_H})
+                    if (ctx->scratch[id].p) CK(cudaMemsetAsync(ctx->scratch[id].p, 0, ctx->scratch[id].cap, ctx->stream));
+                ctx->epoch = 0;
+            }
+            ctx->epoch += 1;
+            CKR(launch_partition(ctx, ord[cur], ord[cur ^ 1], stride, (int)F, d_psegs, d_ptiles, (int)ptiles.size(), pelems,
+                                 d_mask, pstatus, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr, row_mask));
+            cur ^= 1;
+            // the pinned staging area is rewritten by the next level: let the copies finish first
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        live.swap(next_live);
+    }
+    if (single_node_out) return ctx->fail_msg("class_split_node: the node cannot be searched");
+
+    // pre-order ids, left first (base.py:47-52; tree_builder.py:91-94 pushes right, then left)
+    const int64_t count = (int64_t)nodes.size();
+    if (count > capacity) return ctx->fail_msg("fit_classes: tree arrays too small");
+    std::vector<int> new_id(count, -1), stack(1, 0);
+    int next = 0;
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        new_id[v] = next++;
+        if (!nodes[v].leaf) {
+            stack.push_back(nodes[v].right);
+            stack.push_back(nodes[v].left);
+        }
+    }
+    for (int64_t v = 0; v < count; ++v) {
+        const CNode &nd = nodes[v];
+        const int id = new_id[v];
+        if (nd.leaf) {
+            children_left[id] = -1;
+            children_right[id] = -1;
+            feature[id] = -2;
+            threshold[id] = -2.0;
+            value[id] = nd.value;
+        } else {
+            children_left[id] = new_id[nd.left];
+            children_right[id] = new_id[nd.right];
+            feature[id] = nd.feature;
+            threshold[id] = nd.thr;
+            value[id] = 0.0;   // the reference leaves internal values uninitialised (base.py:36)
+        }
+        if (n_node_samples) n_node_samples[id] = nd.n;
+    }
+    *node_count = count;
+    return 0;
+}
+
+extern "C" {
+
+int b200dt_fit_classes(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F, int64_t ldx,
+                       int space, int n_classes, int criterion, int max_depth, double min_improvement,
+                       int64_t min_sample_leaf, int64_t *children_left, int64_t *children_right, int64_t *feature,
+                       double *threshold, double *value, int32_t *n_node_samples, int64_t capacity,
+                       int64_t *node_count) {
+    if (!ctx) return 1;
+    if (!X || !labels || !children_left || !children_right || !feature || !threshold || !value || !node_count)
+        return ctx->fail_msg("fit_classes: null argument");
+    CK(cudaSetDevice(ctx->device));
+    return class_fit_impl(ctx, X, labels, N, F, ldx, space, n_classes, criterion, max_depth, min_improvement,
+                          min_sample_leaf, children_left, children_right, feature, threshold, value, n_node_samples,
+                          capacity, node_count, nullptr);
+}
+
+int b200dt_class_split_node(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t n, int64_t F, int64_t ldx,
+                            int space, int n_classes, int criterion, int64_t *out_f, int64_t *out_k,
+                            double *out_threshold, double *out_score) {
+    if (!ctx) return 1;
+    if (!X || !labels || !out_f || !out_k || !out_threshold || !out_score)
+        return ctx->fail_msg("class_split_node: null argument");
+    if (n < 2) return ctx->fail_msg("class_split_node: attempt to get argmax of an empty sequence (n < 2)");
+    CK(cudaSetDevice(ctx->device));
+    CCand c;
+    int64_t dummy = 0;
+    CKR(class_fit_impl(ctx, X, labels, n, F, ldx, space, n_classes, criterion, 1, 0.0, 0, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, 0, &dummy, &c));
+    *out_f = c.f;
+    *out_k = c.k;
+    *out_threshold = c.threshold;
+    *out_score = c.score;
+    return 0;
+}
+
+}  // extern "C"

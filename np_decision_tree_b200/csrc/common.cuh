@@ -33,13 +33,16 @@ enum KernelClass {
     KC_LEVEL_FUSED,       // fused per-level partition + search of the children (streaming y payload)
     KC_PAYLOAD,           // y payload gather, once after the sort
     KC_SORT_FIXUP,        // 32-bit sort path: gather full keys, repair runs tied on the top 32 bits
+    KC_CLASS_HIST,        // classification: per-tile class histograms
+    KC_CLASS_SCORE,       // classification: gini / precision-at-1 scores + argmax
     KC_COUNT
 };
 
 static const char *const kKernelClassNames[KC_COUNT] = {
     "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
     "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
-    "misc", "level_fused_partition_search", "gather_y_payload", "sort_fixup_ties"};
+    "misc", "level_fused_partition_search", "gather_y_payload", "sort_fixup_ties", "class_tile_histogram",
+    "class_score_search"};
 
 struct DevBuf {
     void *p = nullptr;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
                                                            const u32 *__restrict__ mask, u64 *status, u32 epoch,
-                                                           int n_cols) {
+                                                           int n_cols, int row_mask) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
     const int64_t total_tiles = (int64_t)n_tiles * n_cols;
@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         u32 leftbits = 0;  // bit i: item i of this lane goes left
 #pragma unroll
         for (int i = 0; i < PT_ITEMS; ++i) {
-            const int row = rows[i];
-            const bool is_left = row >= 0 && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
+            // PAY == 3: the class id rides in the bits above row_mask (classes.cu), so the sign bit is data
+            const int row = PAY == 3 ? (rows[i] & row_mask) : rows[i];
+            const bool ok = PAY == 3 ? (i * 32 + lane < cnt) : (row >= 0);
+            const bool is_left = ok && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
             leftbits |= (is_left ? 1u : 0u) << i;
         }
         // every lane sees every ballot, so the tile's left count is register arithmetic; the ballots
@@ -71,14 +73,14 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         for (int i = 0; i < PT_ITEMS; ++i) run += __popc(__ballot_sync(FULL_MASK, (leftbits >> i) & 1u));
         int lb_row = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, run, lane);
         int *ocol = out + cbase;
-        const double *ycol = PAY ? y_in + cbase + off : nullptr;
-        double *oy = PAY ? y_out + cbase : nullptr;
+        const double *ycol = (PAY == 1 || PAY == 2) ? y_in + cbase + off : nullptr;
+        double *oy = (PAY == 1 || PAY == 2) ? y_out + cbase : nullptr;
         const double *wcol = PAY == 2 ? w_in + cbase + off : nullptr;
         double *ow = PAY == 2 ? w_out + cbase : nullptr;
 #pragma unroll
         for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
             double yv[4], wv[4];
-            if (PAY) {
+            if (PAY == 1 || PAY == 2) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int e = (i0 + u) * 32 + lane;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                     const int lb = lb_row + __popc(b & lt);  // left rows before this element
                     const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
                     ocol[dest] = rows[i];
-                    if (PAY) oy[dest] = yv[u];
+                    if (PAY == 1 || PAY == 2) oy[dest] = yv[u];
                     if (PAY == 2) ow[dest] = wv[u];
                 }
                 lb_row += __popc(b);
@@ -124,22 +126,23 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                      u64 *status, u32 epoch, u32 *ticket, const double *y_in, double *y_out, const double *w_in,
-                     double *w_out) {
+                     double *w_out, int packed_row_mask) {
     (void)ticket;
     if (n_tiles <= 0) return 0;
-    const int pay = (y_in && y_out) ? ((w_in && w_out) ? 2 : 1) : 0;
+    const int pay = packed_row_mask ? 3 : (y_in && y_out) ? ((w_in && w_out) ? 2 : 1) : 0;
     const int64_t total = (int64_t)n_tiles * F_store;
     int per_sm = 0;
-    const void *kern = pay == 2 ? (const void *)partition_kernel<2>
-                                : pay == 1 ? (const void *)partition_kernel<1> : (const void *)partition_kernel<0>;
+    const void *kern = pay == 3 ? (const void *)partition_kernel<3>
+                       : pay == 2 ? (const void *)partition_kernel<2>
+                       : pay == 1 ? (const void *)partition_kernel<1> : (const void *)partition_kernel<0>;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
-    const double *yi = pay ? y_in : nullptr, *wi = pay == 2 ? w_in : nullptr;
-    double *yo = pay ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;
+    const double *yi = (pay == 1 || pay == 2) ? y_in : nullptr, *wi = pay == 2 ? w_in : nullptr;
+    double *yo = (pay == 1 || pay == 2) ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;
     void *args[] = {&orders_in, &orders_out, &yi, &yo, &wi, &wo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status,
-                    &epoch, &F_store};
+                    &epoch, &F_store, &packed_row_mask};
     CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
     return 0;
 }

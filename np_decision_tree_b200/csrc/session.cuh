@@ -65,4 +65,4 @@ struct Session {
 };
 
 
-enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1 };
+enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1, PIN_CLASS };

@@ -263,4 +263,4 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                      u64 *status, u32 epoch, u32 *ticket, const double *y_in = nullptr, double *y_out = nullptr,
-                     const double *w_in = nullptr, double *w_out = nullptr);
+                     const double *w_in = nullptr, double *w_out = nullptr, int packed_row_mask = 0);

@@ -1,0 +1,79 @@
+"""Mirror of ``decision_tree/tree_builder.py`` for the exhaustive classification trees.
+
+``build_classification_tree`` keeps the reference's signature and defaults.  The whole fit --
+one sort, then per level the class-count scans, the gini / precision-at-1 scores of every split
+position of every live node, the decisions and the stable partition -- runs on the GPU
+(``b200dt_fit_classes``, csrc/classes.cu) and returns the reference's ``DecisionTree`` with
+pre-order node ids.  Citations are to /root/reference/decision_tree/tree_builder.py.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ._common import context_for, matrix_arg
+from .base import DecisionTree
+from .strategy import (greedy_classification, greedy_classification_p_at_k, random_classify,  # noqa: F401
+                       random_classify_p_at_k, random_split, random_split_v2)
+
+
+def leaf_from_data_regression(y):
+    """tree_builder.py:16-17."""
+    return np.mean(y)
+
+
+def leaf_from_data_classification(y):
+    """tree_builder.py:20-21: first most frequent class of a one-hot block."""
+    return np.argmax(y.sum(axis=0))
+
+
+_CRITERION = {greedy_classification: _lib.GINI, greedy_classification_p_at_k: _lib.P_AT_1}
+
+
+def build_classification_tree(X, y,
+                              max_depth=2,
+                              max_feature=100,
+                              min_improvement=0.01,
+                              min_sample_leaf=1,
+                              split_method=random_classify,
+                              leaf_from_data=leaf_from_data_classification,
+                              max_classes=2):
+    """tree_builder.py:149-159 -> build_tree (:56-96).  ``y`` holds integer class ids in
+    ``[0, max_classes)``.  ``split_method`` must be one of this package's exhaustive searches
+    (the reference's default, ``random_classify``, is not accelerated and raises)."""
+    if split_method not in _CRITERION:
+        split_method()     # raises NotImplementedError for the random splitters
+        raise NotImplementedError("split_method must be greedy_classification or greedy_classification_p_at_k")
+    if leaf_from_data is not leaf_from_data_classification:
+        raise NotImplementedError("classification leaves are the most frequent class (leaf_from_data_classification)")
+    xp, xs, xk, N, F, ldx = matrix_arg(X)
+    if F > max_feature:
+        raise NotImplementedError("F > max_feature samples columns with np.random per node "
+                                  "(tree_builder.py:44-48); pass max_feature >= X.shape[1]")
+    if hasattr(y, "data_ptr") and not isinstance(y, np.ndarray):
+        import torch
+        lab = y.to(torch.int32).contiguous()
+        lp, ls, lk = _lib.as_arg(lab, np.int32, "y")
+    else:
+        lab = np.asarray(y)
+        if lab.ndim != 1 or not np.issubdtype(lab.dtype, np.integer):
+            raise IndexError("y must be a 1-D array of integer class ids (it indexes np.eye(max_classes))")
+        if lab.size and (lab.min() < -max_classes or lab.max() >= max_classes):
+            raise IndexError(f"index out of bounds for axis 0 with size {max_classes}")   # np.eye(C)[y]
+        lab = np.ascontiguousarray(np.where(lab < 0, lab + max_classes, lab), dtype=np.int32)
+        lp, ls, lk = lab.ctypes.data, _lib.HOST, lab
+    if xs != ls:
+        raise ValueError("X and y must both be host arrays or both be CUDA tensors")
+    if int(lab.shape[0]) != N:
+        raise ValueError(f"y has {int(lab.shape[0])} entries, X has {N} rows")
+    ctx = context_for(X, y)
+    tree = DecisionTree(2 ** (max_depth + 1))
+    t = tree.tree_
+    count = ctypes.c_int64(0)
+    ctx.check(ctx.lib.b200dt_fit_classes(
+        ctx.handle, xp, lp, N, F, ldx, xs, int(max_classes), _CRITERION[split_method], int(max_depth),
+        float(min_improvement), int(min_sample_leaf), t.children_left.ctypes.data, t.children_right.ctypes.data,
+        t.feature.ctypes.data, t.threshold.ctypes.data, t.value.ctypes.data, None, t.feature.shape[0],
+        ctypes.byref(count)))
+    tree.max_node_ = int(count.value) - 1
+    return tree.final()

@@ -132,3 +132,21 @@ def test_shard_columns():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_classification_mirror_rejects_what_is_not_accelerated():
+    """Host-side argument checks of the tree_builder mirror run before any GPU work."""
+    import numpy as np
+    import pytest
+    from np_decision_tree_b200.decision_tree import strategy, tree_builder
+    X = np.random.RandomState(0).standard_normal((20, 5))
+    y = np.arange(20) % 2
+    with pytest.raises(NotImplementedError, match="random"):
+        tree_builder.build_classification_tree(X, y)                       # reference default: random_classify
+    with pytest.raises(NotImplementedError, match="max_feature"):
+        tree_builder.build_classification_tree(X, y, max_feature=3, split_method=strategy.greedy_classification)
+    with pytest.raises(IndexError):
+        tree_builder.build_classification_tree(X, y + 5, split_method=strategy.greedy_classification)
+    with pytest.raises(ValueError, match="one-hot"):
+        strategy.greedy_classification(X, np.ones((20, 2)))
+    assert strategy.surrogate_to_gini(30.0, np.eye(2)[y]) == 30.0 / 20 - 0.5

@@ -1,0 +1,137 @@
+"""Classification trees on the GPU (csrc/classes.cu through b200dt_fit_classes /
+b200dt_class_split_node) against the reference-generated goldens and the numpy oracle.
+Integer class statistics: every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from util import GoldenTree, assert_same_tree
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["g0", "g1", "g2", "g3", "g4", "g5", "gk", "p0", "p1", "p2", "pk"]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from np_decision_tree_b200.decision_tree import strategy, tree_builder, utils
+    return strategy, tree_builder, utils
+
+
+def method_of(strategy, criterion):
+    return strategy.greedy_classification if criterion == "gini" else strategy.greedy_classification_p_at_k
+
+
+def class_problem(seed, n, F, C, noise=0.5, integer_features=None):
+    rs = np.random.RandomState(seed)
+    X = rs.standard_normal((n, F))
+    W = rs.standard_normal((F, C)) * (rs.uniform(size=(F, 1)) < 0.6)
+    labels = np.argmax(X @ W + noise * rs.standard_normal((n, C)), axis=1).astype(np.int64)
+    if integer_features:
+        X = np.round(X * integer_features)          # heavy ties inside every column
+    return X, labels
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tree_matches_reference_golden(golden_classes, mods, name):
+    strategy, tree_builder, utils = mods
+    g, p = golden_classes, f"cl_{name}_"
+    C, F = int(g[p + "classes"]), g[p + "X"].shape[1]
+    t = tree_builder.build_classification_tree(
+        g[p + "X"], g[p + "labels"], max_depth=int(g[p + "depth"]), max_feature=F,
+        min_improvement=float(g[p + "min_improvement"]), min_sample_leaf=int(g[p + "min_sample_leaf"]),
+        split_method=method_of(strategy, str(g[p + "criterion"])), max_classes=C)
+    assert_same_tree(t, GoldenTree(g, p), leaf_rtol=0.0, what=name)
+    assert np.array_equal(utils.inference(g[p + "X"], t), g[p + "pred"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_root_search_matches_reference_golden(golden_classes, mods, name):
+    strategy, _, _ = mods
+    g, p = golden_classes, f"cl_{name}_"
+    C = int(g[p + "classes"])
+    col, thr, imp, const = method_of(strategy, str(g[p + "criterion"]))(g[p + "X"], np.eye(C)[g[p + "labels"]])
+    want = g[p + "root"]
+    assert (col, thr) == (int(want[0]), want[1])
+    assert imp == want[2]
+    assert const.dtype == bool and const.shape == (g[p + "X"].shape[1],) and not const.any()
+
+
+@pytest.mark.parametrize("criterion", ["gini", "p_at_k"])
+@pytest.mark.parametrize("seed,n,F,C,depth,ties", [
+    (1, 5000, 16, 7, 10, None),        # several 1024-row tiles per node
+    (2, 3000, 5, 64, 8, None),         # two 32-class chunks
+    (3, 2500, 4, 200, 6, None),        # seven chunks
+    (4, 4000, 6, 3, 9, 3.0),           # repeated feature values: value-based split extends the tie run
+    (5, 1025, 3, 2, 12, None),         # one row past a tile boundary
+    (6, 2048, 2, 4, 5, 1.0),
+])
+def test_tree_matches_oracle(mods, criterion, seed, n, F, C, depth, ties):
+    strategy, tree_builder, utils = mods
+    X, labels = class_problem(seed, n, F, C, integer_features=ties)
+    kw = dict(max_depth=depth, max_feature=F, min_improvement=1e-7, min_sample_leaf=1)
+    want = oracle.fit_classes(X, labels, C, criterion=criterion, sort_kind="stable", **kw)
+    got = tree_builder.build_classification_tree(X, labels, split_method=method_of(strategy, criterion),
+                                                 max_classes=C, **kw)
+    assert_same_tree(got, want, leaf_rtol=0.0, what=f"{criterion} seed {seed}")
+    assert np.array_equal(utils.inference(X, got), oracle.predict(X, want))
+
+
+def test_larger_node_counts_match_oracle(mods):
+    strategy, tree_builder, _ = mods
+    X, labels = class_problem(11, 200_000, 8, 5)
+    kw = dict(max_depth=6, max_feature=8, min_improvement=1e-7)
+    want = oracle.fit_classes(X, labels, 5, **kw)
+    got = tree_builder.build_classification_tree(X, labels, split_method=strategy.greedy_classification,
+                                                 max_classes=5, **kw)
+    assert_same_tree(got, want, leaf_rtol=0.0)
+
+
+def test_pure_node_is_a_leaf_and_depth_zero(mods):
+    strategy, tree_builder, _ = mods
+    X = np.random.RandomState(0).standard_normal((50, 3))
+    t = tree_builder.build_classification_tree(X, np.full(50, 2), split_method=strategy.greedy_classification,
+                                               max_classes=4)
+    assert t.max_node_ == 0 and t.tree_.value[0] == 2.0 and t.tree_.children_left[0] == -1
+    labels = (X[:, 1] > 0).astype(np.int64)
+    t = tree_builder.build_classification_tree(X, labels, max_depth=0, split_method=strategy.greedy_classification)
+    assert t.max_node_ == 0 and t.tree_.value[0] == float(np.argmax(np.bincount(labels)))
+    # min_improvement = 0 lets a pure node split at the first position of column 0, like the reference
+    want = oracle.fit_classes(X, np.zeros(50, dtype=np.int64), 2, max_depth=2, min_improvement=0.0)
+    got = tree_builder.build_classification_tree(X, np.zeros(50, dtype=np.int64), max_depth=2, min_improvement=0.0,
+                                                 split_method=strategy.greedy_classification)
+    assert_same_tree(got, want, leaf_rtol=0.0)
+
+
+def test_all_rows_on_one_side(mods):
+    # a constant column chosen at position 0 sends every row left; the right child is an empty leaf of class 0
+    strategy, tree_builder, _ = mods
+    X = np.ones((40, 1))
+    labels = np.arange(40) % 2
+    kw = dict(max_depth=2, max_feature=1, min_improvement=-1.0)
+    want = oracle.fit_classes(X, labels, 2, sort_kind="stable", **kw)
+    got = tree_builder.build_classification_tree(X, labels, split_method=strategy.greedy_classification, **kw)
+    assert_same_tree(got, want, leaf_rtol=0.0)
+
+
+def test_torch_cuda_inputs(mods):
+    import torch
+    strategy, tree_builder, _ = mods
+    X, labels = class_problem(21, 3000, 6, 4)
+    kw = dict(max_depth=6, max_feature=6, min_improvement=1e-7, split_method=strategy.greedy_classification,
+              max_classes=4)
+    host = tree_builder.build_classification_tree(X, labels, **kw)
+    dev = tree_builder.build_classification_tree(torch.from_numpy(X).cuda(), torch.from_numpy(labels).cuda(), **kw)
+    assert_same_tree(dev, host, leaf_rtol=0.0)
+
+
+def test_errors(mods):
+    strategy, tree_builder, _ = mods
+    from np_decision_tree_b200._lib import B200Error
+    X, labels = class_problem(31, 100, 4, 3)
+    with pytest.raises(B200Error, match="n_classes"):
+        tree_builder.build_classification_tree(X, labels, split_method=strategy.greedy_classification,
+                                               max_classes=300)
+    with pytest.raises(B200Error, match="single row"):
+        tree_builder.build_classification_tree(X, labels, max_depth=12, min_sample_leaf=0, min_improvement=-1.0,
+                                               split_method=strategy.greedy_classification, max_classes=3)
