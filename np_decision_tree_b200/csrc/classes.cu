@@ -29,6 +29,7 @@
 
 #include <math_constants.h>
 
+#include "class_div.cuh"
 #include "session.cuh"
 
 constexpr int GT_ROWS = 32;
@@ -262,8 +263,8 @@ __global__ void __launch_bounds__(256) class_score_kernel(const u32 *__restrict_
                     const long long SL = a_run + (long long)a;
                     const long long SR = sg.st2 - 2 * (b_run + (long long)b) + SL;
                     // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
-                    const double sc = __dadd_rn(__ddiv_rn((double)SL, (double)(kk + 1)),
-                                                __ddiv_rn((double)SR, (double)(n - kk - 1)));
+                    const double sc = __dadd_rn(div_counts((double)SL, (double)(kk + 1)),
+                                                div_counts((double)SR, (double)(n - kk - 1)));
                     if (sc > best) {
                         best = sc;
                         best_k = kk;
@@ -331,52 +332,191 @@ __global__ void __launch_bounds__(256) class_score_kernel(const u32 *__restrict_
     }
 }
 
+// ---- pass 3, gini with at most 32 classes: lane-contiguous scoring ---------------------------
+// Each lane owns 32 CONSECUTIVE positions of the tile, so the running sums are plain per-lane
+// registers and no per-row warp scan is needed.  A lane's class counters {L_c, R_c = T_c - L_c}
+// live in shared memory as one 64-bit word per (class, lane) (bank = lane: conflict-free); their
+// start values come from one warp scan per class over the lanes' chunk histograms.  Adding a
+// row of class c moves sum_c L_c^2 by 2 L_c + 1 and sum_c R_c^2 by -(2 R_c - 1).
+constexpr int LANE_MAX_CLASSES = 32;
+constexpr int STAGE_PITCH = 33;
+
+__global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__restrict__ orders, int64_t col_stride,
+                                                               const CSeg *__restrict__ segs,
+                                                               const TileDesc *__restrict__ tiles, int n_tiles, int F,
+                                                               int C, int row_bits, const int *__restrict__ excl,
+                                                               const int *__restrict__ tot,
+                                                               CPart *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8;
+    u64 *pk = reinterpret_cast<u64 *>(smraw + warp * per_warp);             // [C][32] {L (low), R (high)}
+    u32 *stage = reinterpret_cast<u32 *>(smraw + warp * per_warp + (size_t)C * 32 * 8);  // [32][33]
+    const int64_t total = (int64_t)n_tiles * F;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total; t += (int64_t)gridDim.x * 8) {
+        const int f = (int)(t % F), ti = (int)(t / F);
+        const TileDesc td = tiles[ti];
+        const CSeg sg = segs[td.seg];
+        const int off = td.tin * GT_TILE;
+        const int n = sg.n;
+        const int cnt_here = min(GT_TILE, n - off);
+        const u32 *col = orders + (int64_t)f * col_stride + sg.start + off;
+        // coalesced load, transposed through shared memory: element e -> stage[e / 32][e % 32]
+#pragma unroll
+        for (int i = 0; i < GT_ROWS; ++i)
+            stage[i * STAGE_PITCH + lane] = (i * 32 + lane < cnt_here) ? ld_stream_u32(col + i * 32 + lane) : 0xffffffffu;
+        for (int c = 0; c < C; ++c) pk[c * 32 + lane] = 0ull;
+        __syncwarp();
+        const int my0 = lane * 32;                       // first position of this lane inside the tile
+        const int mine = max(0, min(32, cnt_here - my0));  // valid positions of this lane
+        const u32 *my = stage + lane * STAGE_PITCH;
+        u32 *pk32 = reinterpret_cast<u32 *>(pk);
+        for (int j = 0; j < mine; ++j) {
+            const int c = (int)(my[j] >> row_bits);
+            pk32[(c * 32 + lane) * 2] += 1u;
+        }
+        // start counts of every class for this lane: counts at the tile start + the earlier lanes' rows
+        const int *ex = excl + ((int64_t)f * n_tiles + ti) * C;
+        const int *tt = tot + (int64_t)td.seg * C;
+        long long SL = 0, SR = 0;
+        for (int c = 0; c < C; ++c) {
+            const int h = (int)pk32[(c * 32 + lane) * 2];
+            int inc = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(FULL_MASK, inc, d);
+                if (lane >= d) inc += u;
+            }
+            const int L0 = __ldg(ex + c) + inc - h;
+            const int R0 = __ldg(tt + c) - L0;
+            pk[c * 32 + lane] = (u64)(u32)L0 | ((u64)(u32)R0 << 32);
+            SL += (long long)L0 * L0;
+            SR += (long long)R0 * R0;
+        }
+        double best = -CUDART_INF;
+        int best_k = 0x7fffffff;
+        for (int j = 0; j < mine; ++j) {
+            const int c = (int)(my[j] >> row_bits);
+            const u64 w = pk[c * 32 + lane];
+            const int L = (int)(u32)w, R = (int)(u32)(w >> 32);
+            SL += 2ll * L + 1;
+            SR -= 2ll * R - 1;
+            pk[c * 32 + lane] = (u64)(u32)(L + 1) | ((u64)(u32)(R - 1) << 32);
+            const int kk = off + my0 + j;
+            if (kk < n - 1) {
+                // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
+                const double sc = __dadd_rn(div_counts((double)SL, (double)(kk + 1)),
+                                            div_counts((double)SR, (double)(n - kk - 1)));
+                if (sc > best) {   // positions increase: strict ">" keeps the lowest one
+                    best = sc;
+                    best_k = kk;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ob = shfl_xor_d(best, m);
+            const int ok2 = __shfl_xor_sync(FULL_MASK, best_k, m);
+            if (ob > best || (ob == best && ok2 < best_k)) {
+                best = ob;
+                best_k = ok2;
+            }
+        }
+        if (lane == 0) {
+            CPart p;
+            p.score = best;
+            p.k = best_k;
+            p.pad = 0;
+            partials[(int64_t)f * n_tiles + ti] = p;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- per-node arg-best over (tile, column): flat row-major rule (position, then column) -----
 // strategy.py:277-278: np.unravel_index(np.argmax(improvements), shape) on an (n-1, F) array
-__global__ void __launch_bounds__(256) class_finalize_kernel(const CSeg *__restrict__ segs, int F, int n_tiles,
-                                                             const CPart *__restrict__ partials,
-                                                             const u32 *__restrict__ orders, int64_t col_stride,
-                                                             int row_mask, const double *__restrict__ X, int64_t ldx,
-                                                             CCand *__restrict__ out) {
+constexpr int CF_SLICES = 64;
+
+struct CBest {
+    double score;
+    int k, f;
+};
+
+__device__ __forceinline__ bool cbest_better(double os, int ok, int of, double ms, int mk, int mf) {
+    if (ok == 0x7fffffff) return false;
+    if (mk == 0x7fffffff) return true;
+    return os > ms || (os == ms && (ok < mk || (ok == mk && of < mf)));
+}
+
+// block-wide reduction of one candidate per thread; result valid in thread 0
+__device__ __forceinline__ CBest cbest_block_reduce(CBest mine) {
     __shared__ double s_score[256];
     __shared__ int s_k[256], s_f[256];
-    const CSeg sg = segs[blockIdx.x];
-    double best = -CUDART_INF;
-    int bk = 0x7fffffff, bf = 0x7fffffff;
-    const int64_t n_rec = (int64_t)sg.ntiles * F;
-    for (int64_t r = threadIdx.x; r < n_rec; r += 256) {
-        const int f = (int)(r / sg.ntiles), tt = (int)(r % sg.ntiles);
-        const CPart p = partials[(int64_t)f * n_tiles + sg.tile_base + tt];
-        if (p.k == 0x7fffffff) continue;
-        if (p.score > best || (p.score == best && (p.k < bk || (p.k == bk && f < bf)))) {
-            best = p.score;
-            bk = p.k;
-            bf = f;
-        }
-    }
-    s_score[threadIdx.x] = best;
-    s_k[threadIdx.x] = bk;
-    s_f[threadIdx.x] = bf;
+    s_score[threadIdx.x] = mine.score;
+    s_k[threadIdx.x] = mine.k;
+    s_f[threadIdx.x] = mine.f;
     __syncthreads();
     for (int m = 128; m >= 1; m >>= 1) {
-        if ((int)threadIdx.x < m) {
-            const double os = s_score[threadIdx.x + m];
-            const int ok = s_k[threadIdx.x + m], of = s_f[threadIdx.x + m];
-            const double ms = s_score[threadIdx.x];
-            const int mk = s_k[threadIdx.x], mf = s_f[threadIdx.x];
-            if (ok != 0x7fffffff && (mk == 0x7fffffff || os > ms || (os == ms && (ok < mk || (ok == mk && of < mf))))) {
-                s_score[threadIdx.x] = os;
-                s_k[threadIdx.x] = ok;
-                s_f[threadIdx.x] = of;
-            }
+        if ((int)threadIdx.x < m &&
+            cbest_better(s_score[threadIdx.x + m], s_k[threadIdx.x + m], s_f[threadIdx.x + m], s_score[threadIdx.x],
+                         s_k[threadIdx.x], s_f[threadIdx.x])) {
+            s_score[threadIdx.x] = s_score[threadIdx.x + m];
+            s_k[threadIdx.x] = s_k[threadIdx.x + m];
+            s_f[threadIdx.x] = s_f[threadIdx.x + m];
         }
         __syncthreads();
     }
+    CBest r;
+    r.score = s_score[0];
+    r.k = s_k[0];
+    r.f = s_f[0];
+    return r;
+}
+
+// stage 1: grid (n_live, CF_SLICES): every block reduces one slice of the node's records
+__global__ void __launch_bounds__(256) class_finalize_slices_kernel(const CSeg *__restrict__ segs, int F, int n_tiles,
+                                                                    const CPart *__restrict__ partials,
+                                                                    CBest *__restrict__ sliced) {
+    const CSeg sg = segs[blockIdx.x];
+    const int64_t n_rec = (int64_t)sg.ntiles * F;
+    const int64_t per = (n_rec + CF_SLICES - 1) / CF_SLICES;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(n_rec, r0 + per);
+    CBest b;
+    b.score = -CUDART_INF;
+    b.k = 0x7fffffff;
+    b.f = 0x7fffffff;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+        const int f = (int)(r / sg.ntiles), tt = (int)(r % sg.ntiles);
+        const CPart p = partials[(int64_t)f * n_tiles + sg.tile_base + tt];
+        if (cbest_better(p.score, p.k, f, b.score, b.k, b.f)) {
+            b.score = p.score;
+            b.k = p.k;
+            b.f = f;
+        }
+    }
+    b = cbest_block_reduce(b);
+    if (threadIdx.x == 0) sliced[(int64_t)blockIdx.x * CF_SLICES + blockIdx.y] = b;
+}
+
+// stage 2: one block per node: best slice, then threshold and the end of its run of equal values
+__global__ void __launch_bounds__(256) class_finalize_kernel(const CSeg *__restrict__ segs,
+                                                             const CBest *__restrict__ sliced,
+                                                             const u32 *__restrict__ orders, int64_t col_stride,
+                                                             int row_mask, const double *__restrict__ X, int64_t ldx,
+                                                             CCand *__restrict__ out) {
+    const CSeg sg = segs[blockIdx.x];
+    CBest b;
+    b.score = -CUDART_INF;
+    b.k = 0x7fffffff;
+    b.f = 0x7fffffff;
+    if (threadIdx.x < CF_SLICES) b = sliced[(int64_t)blockIdx.x * CF_SLICES + threadIdx.x];
+    b = cbest_block_reduce(b);
     if (threadIdx.x == 0) {
         CCand c;
-        c.score = s_score[0];
-        c.k = s_k[0];
-        c.f = s_f[0];
+        c.score = b.score;
+        c.k = b.k;
+        c.f = b.f;
         c.k_ext = c.k;
         c.threshold = 0.0;
         c.pad = 0;
@@ -637,7 +777,15 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
                                                              criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
         }
         CK(cudaGetLastError());
-        {
+        if (criterion == B200DT_GINI && C <= LANE_MAX_CLASSES) {
+            const size_t smem = (size_t)8 * ((size_t)32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
+            const void *kern = (const void *)class_score_lane_kernel;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = resident_grid(ctx, kern, smem, work);
+            LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
+            class_score_lane_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
+                                                                      row_bits, d_excl, d_tot, d_part);
+        } else {
             const bool patk = criterion == B200DT_P_AT_1;
             const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;
             const void *kern = patk ? (const void *)class_score_kernel<1> : (const void *)class_score_kernel<0>;
@@ -653,9 +801,13 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         }
         CK(cudaGetLastError());
         {
-            LaunchScope ls(ctx, KC_FINALIZE, (double)work * sizeof(CPart));
-            class_finalize_kernel<<<n_live, 256, 0, ctx->stream>>>(d_segs, (int)F, n_tiles, d_part, d_ord, stride, row_mask,
-                                                                   dX, dld, d_cand);
+            CBest *d_sliced;
+            CKR(scratch_get(ctx, SB_L1_G, (size_t)n_live * CF_SLICES * sizeof(CBest) + 64, (void **)&d_sliced));
+            LaunchScope ls(ctx, KC_FINALIZE, (double)work * sizeof(CPart), 2);
+            class_finalize_slices_kernel<<<dim3(n_live, CF_SLICES), 256, 0, ctx->stream>>>(d_segs, (int)F, n_tiles, d_part,
+                                                                                         d_sliced);
+            class_finalize_kernel<<<n_live, 256, 0, ctx->stream>>>(d_segs, d_sliced, d_ord, stride, row_mask, dX, dld,
+                                                                   d_cand);
         }
         CK(cudaGetLastError());
         CCand *h_cand;

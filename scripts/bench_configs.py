@@ -1,11 +1,13 @@
 """Side measurements of the other BASELINE.json configs (bench.py carries only the headline, C4).
 
-    python scripts/bench_configs.py [c2] [c3] [c5] [--cpu]
+    python scripts/bench_configs.py [c2] [c3] [c5] [cls] [--cpu]
 
 C2: make_regression 10 000 x 100, L2 depth 10 fit + inference (README.md:60-64: 390 ms reference)
 C3: L1 build_regression_tree_v2 depth 1, 1 M x 100 (cummedian path; BASELINE.md: 138 s on one core)
 C5: inference of a depth-10 tree, N x 256 device-resident rows on one GPU (row-sharded across GPUs
     with no exchange, so N per GPU is what matters; default 12.5 M = the 8-GPU share of 100 M)
+cls: exhaustive gini (CLS_CRIT=p_at_k: precision-at-1) classification fit, depth 10, CLS_ROWS x CLS_FEATURES
+    device-resident rows, CLS_CLASSES classes (defaults 10 M x 256, 8)
 """
 import json
 import os
@@ -108,5 +110,37 @@ if "c5" in args:
         oracle.predict(Xc, tree)
         dt = time.perf_counter() - t0
         out["c5"]["cpu_port_rows_per_s_on_2M_rows"] = 2_000_000 / dt
+
+if "cls" in args:
+    # classification: exhaustive gini fit, device-resident, depth 10
+    from np_decision_tree_b200.decision_tree import strategy, tree_builder
+    N = int(os.environ.get("CLS_ROWS", 10_000_000))
+    F = int(os.environ.get("CLS_FEATURES", 256))
+    C = int(os.environ.get("CLS_CLASSES", 8))
+    crit = strategy.greedy_classification_p_at_k if os.environ.get("CLS_CRIT") == "p_at_k" else strategy.greedy_classification
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    X = torch.empty((N, F), dtype=torch.float64, device="cuda")
+    for c0 in range(0, F, 32):
+        X[:, c0:c0 + 32] = torch.randn((N, min(32, F - c0)), dtype=torch.float64, device="cuda", generator=g)
+    score = X[:, :C] + 0.5 * torch.randn((N, C), dtype=torch.float64, device="cuda", generator=g)
+    labels = score.argmax(dim=1).to(torch.int32)
+    del score
+    kw = dict(max_depth=10, max_feature=F, min_improvement=1e-7, split_method=crit, max_classes=C)
+    tree_builder.build_classification_tree(X, labels, **kw)
+    ctx = _lib.default_context(0)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    t_fit, tree = best_of(lambda: tree_builder.build_classification_tree(X, labels, **kw), n=3)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    pred = utils.inference(X[:1_000_000], tree)
+    out["cls"] = {"rows": N, "features": F, "classes": C, "criterion": crit.__name__, "fit_ms_device_in": t_fit * 1e3,
+                  "rows_features_per_s": N * F / t_fit, "nodes": tree.max_node_ + 1,
+                  "train_accuracy_1M": float((torch.as_tensor(pred, device="cuda") == labels[:1_000_000]).double().mean()),
+                  "kernels_ms_per_fit": {k: round(v["ms"] / 3, 3) for k, v in prof.items() if v["launches"]},
+                  "kernels_alg_gbs": {k: round(v["alg_bytes"] / v["ms"] / 1e6, 1) for k, v in prof.items()
+                                      if v["launches"] and v["alg_bytes"] > 0}}
+    del X, labels
 
 print(json.dumps(out, indent=1))
