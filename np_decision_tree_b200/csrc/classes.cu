@@ -23,6 +23,7 @@
 // Algorithmic bytes: 2 x 4 per live (row, feature) per level (+ 4 + 1 + 4 for the partition).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -341,11 +342,18 @@ __global__ void __launch_bounds__(256) class_score_kernel(const u32 *__restrict_
 constexpr int LANE_MAX_CLASSES = 32;
 constexpr int STAGE_PITCH = 33;
 
+//
+// LB = true: single pass.  The class counts at the tile start come from a decoupled look-back along
+// the tiles of the (node, column) -- lane c carries class c, one tagged 64-bit status word per
+// (tile, column, class) as in lookback_count -- instead of the histogram + scan passes.  The grid
+// must be co-resident and tiles are taken in tile-major order (a tile's predecessor has a smaller
+// work index), exactly like the L2 scan (l2.cu).
+template <bool LB>
 __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__restrict__ orders, int64_t col_stride,
                                                                const CSeg *__restrict__ segs,
                                                                const TileDesc *__restrict__ tiles, int n_tiles, int F,
                                                                int C, int row_bits, const int *__restrict__ excl,
-                                                               const int *__restrict__ tot,
+                                                               const int *__restrict__ tot, u64 *status, u32 epoch,
                                                                CPart *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -376,18 +384,62 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
             pk32[(c * 32 + lane) * 2] += 1u;
         }
         // start counts of every class for this lane: counts at the tile start + the earlier lanes' rows
-        const int *ex = excl + ((int64_t)f * n_tiles + ti) * C;
+        const int *ex = LB ? nullptr : excl + ((int64_t)f * n_tiles + ti) * C;
         const int *tt = tot + (int64_t)td.seg * C;
+        int base = 0;  // LB: lane c holds the count of class c at the tile start
+        if (LB) {
+            int my_agg = 0;
+            for (int c = 0; c < C; ++c) {
+                const int h = (int)pk32[(c * 32 + lane) * 2];
+                int inc = h;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, inc, d);
+                    if (lane >= d) inc += u;
+                }
+                pk32[(c * 32 + lane) * 2 + 1] = (u32)(inc - h);   // rows of class c in the earlier lanes
+                const int agg = __shfl_sync(FULL_MASK, inc, 31);
+                if (lane == c) my_agg = agg;
+            }
+            const u64 tag = (u64)(epoch & 0x3fffffffu) << 32;
+            u64 *st = status + ((int64_t)f * n_tiles + ti) * C + lane;
+            const bool has_class = lane < C;
+            if (td.tin == 0) {
+                if (has_class) st_relaxed_u64(st, (2ull << 62) | tag | (u32)my_agg);
+            } else {
+                if (has_class) st_relaxed_u64(st, (1ull << 62) | tag | (u32)my_agg);
+                bool done = !has_class;
+                const u64 *look = st - C;
+                while (__any_sync(FULL_MASK, !done)) {
+                    if (!done) {
+                        const u64 w = ld_relaxed_u64(look);
+                        if ((w & 0x3fffffff00000000ull) == tag && (w >> 62) != 0) {
+                            base += (int)(u32)w;
+                            if ((w >> 62) == 2)
+                                done = true;
+                            else
+                                look -= C;
+                        }
+                    }
+                }
+                if (has_class) st_relaxed_u64(st, (2ull << 62) | tag | (u32)(base + my_agg));
+            }
+        }
         long long SL = 0, SR = 0;
         for (int c = 0; c < C; ++c) {
-            const int h = (int)pk32[(c * 32 + lane) * 2];
-            int inc = h;
+            int L0;
+            if (LB) {
+                L0 = __shfl_sync(FULL_MASK, base, c) + (int)pk32[(c * 32 + lane) * 2 + 1];
+            } else {
+                const int h = (int)pk32[(c * 32 + lane) * 2];
+                int inc = h;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int u = __shfl_up_sync(FULL_MASK, inc, d);
-                if (lane >= d) inc += u;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, inc, d);
+                    if (lane >= d) inc += u;
+                }
+                L0 = __ldg(ex + c) + inc - h;
             }
-            const int L0 = __ldg(ex + c) + inc - h;
             const int R0 = __ldg(tt + c) - L0;
             pk[c * 32 + lane] = (u64)(u32)L0 | ((u64)(u32)R0 << 32);
             SL += (long long)L0 * L0;
@@ -603,6 +655,17 @@ int upload_vec(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const std::vector<
     return 0;
 }
 
+// advance the look-back epoch (shared with fit.cu's status buffers); on wrap-around clear them first
+int class_next_epoch(b200dt_ctx *ctx) {
+    if (ctx->epoch >= (1u << 30) - 2) {
+        for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_VAL2, SB_STATUS_P, SB_L1_H})
+            if (ctx->scratch[id].p) CK(cudaMemsetAsync(ctx->scratch[id].p, 0, ctx->scratch[id].cap, ctx->stream));
+        ctx->epoch = 0;
+    }
+    ctx->epoch += 1;
+    return 0;
+}
+
 int resident_grid(b200dt_ctx *ctx, const void *kern, size_t smem, int64_t work_warps) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -701,6 +764,9 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         live.push_back(0);
     }
 
+    // B200DT_CLASS_3PASS=1 forces the histogram + scan + score passes (the path of C > 32 and precision-at-1)
+    const char *env3 = getenv("B200DT_CLASS_3PASS");
+    const bool three_pass_env = env3 && env3[0] == '1';
     std::vector<CSeg> segs;
     std::vector<TileDesc> tiles;
     std::vector<int> tot, marks;
@@ -751,6 +817,11 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         CKR(scratch_get(ctx, SB_L1_C, (size_t)n_tiles * F * 4 + 64, (void **)&d_rmax));
         CKR(scratch_get(ctx, SB_PARTIAL, (size_t)n_tiles * F * sizeof(CPart) + 64, (void **)&d_part));
         CKR(scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(CCand) + 64, (void **)&d_cand));
+        int64_t stride_arg = stride;   // (non-const copies: their addresses go into a void* launch list)
+        const CSeg *d_segs_c = d_segs;
+        const TileDesc *d_tiles_c = d_tiles;
+        const int *d_excl_c = d_excl, *d_tot_c = d_tot;
+        int n_tiles_arg = n_tiles;
         size_t po = 0;
         CKR(upload_vec(ctx, PIN_CLASS, po, segs, d_segs));
         po += segs.size() * sizeof(CSeg) + 64;
@@ -761,30 +832,50 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
 
         const u32 *d_ord = (const u32 *)ord[cur];
         const int64_t work = (int64_t)n_tiles * F;
-        {
-            const size_t smem = (size_t)8 * (C + 1) * 4;
-            const int grid = resident_grid(ctx, (const void *)class_hist_kernel, smem, work);
-            LaunchScope ls(ctx, KC_CLASS_HIST, 4.0 * (double)elems * F);
-            class_hist_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
-                                                                row_bits, d_hist);
+        const bool single_pass = criterion == B200DT_GINI && C <= LANE_MAX_CLASSES && !three_pass_env;
+        if (!single_pass) {
+            {
+                const size_t smem = (size_t)8 * (C + 1) * 4;
+                const int grid = resident_grid(ctx, (const void *)class_hist_kernel, smem, work);
+                LaunchScope ls(ctx, KC_CLASS_HIST, 4.0 * (double)elems * F);
+                class_hist_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
+                                                                    row_bits, d_hist);
+            }
+            CK(cudaGetLastError());
+            {
+                const int64_t warps = (int64_t)n_live * F;
+                const int grid =
+                    (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16));
+                LaunchScope ls(ctx, KC_MISC, 8.0 * (double)hist_elems);
+                class_scan_kernel<<<grid, 256, 0, ctx->stream>>>(d_segs, n_live, (int)F, C, n_tiles, d_tot, d_hist, d_excl,
+                                                                 criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
+            }
+            CK(cudaGetLastError());
         }
-        CK(cudaGetLastError());
-        {
-            const int64_t warps = (int64_t)n_live * F;
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16));
-            LaunchScope ls(ctx, KC_MISC, 8.0 * (double)hist_elems);
-            class_scan_kernel<<<grid, 256, 0, ctx->stream>>>(d_segs, n_live, (int)F, C, n_tiles, d_tot, d_hist, d_excl,
-                                                             criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
-        }
-        CK(cudaGetLastError());
         if (criterion == B200DT_GINI && C <= LANE_MAX_CLASSES) {
             const size_t smem = (size_t)8 * ((size_t)32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
-            const void *kern = (const void *)class_score_lane_kernel;
+            const void *kern = single_pass ? (const void *)class_score_lane_kernel<true>
+                                           : (const void *)class_score_lane_kernel<false>;
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = resident_grid(ctx, kern, smem, work);
+            u64 *d_status = nullptr;
+            u32 epoch = 0;
+            if (single_pass) {
+                CKR(scratch_get(ctx, SB_STATUS_F, ((size_t)work * C + 1) * 8, (void **)&d_status, true));
+                CKR(class_next_epoch(ctx));
+                epoch = ctx->epoch;
+            }
+            int Fi = (int)F;
+            CPart *d_part_arg = d_part;
+            void *args[] = {&d_ord, &stride_arg, &d_segs_c, &d_tiles_c, &n_tiles_arg, &Fi, &C, &row_bits, &d_excl_c,
+                            &d_tot_c, &d_status, &epoch, &d_part_arg};
             LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
-            class_score_lane_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
-                                                                      row_bits, d_excl, d_tot, d_part);
+            if (single_pass)
+                CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));   // tiles wait on earlier tiles
+            else
+                class_score_lane_kernel<false><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, Fi,
+                                                                                 C, row_bits, d_excl, d_tot, nullptr, 0u,
+                                                                                 d_part);
         } else {
             const bool patk = criterion == B200DT_P_AT_1;
             const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;
@@ -940,12 +1031,7 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
             po += psegs.size() * sizeof(SegDev) + 64;
             CKR(upload_vec(ctx, PIN_CLASS, po, ptiles, d_ptiles));
             CKR(scratch_get(ctx, SB_STATUS_P, (ptiles.size() * (size_t)F + 1) * 8, (void **)&pstatus, true));
-            if (ctx->epoch >= (1u << 30) - 2) {
-                for (int id : {SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_VAL2, SB_STATUS_P, SB_L1_H})
-                    if (ctx->scratch[id].p) CK(cudaMemsetAsync(ctx->scratch[id].p, 0, ctx->scratch[id].cap, ctx->stream));
-                ctx->epoch = 0;
-            }
-            ctx->epoch += 1;
+            CKR(class_next_epoch(ctx));
             CKR(launch_partition(ctx, ord[cur], ord[cur ^ 1], stride, (int)F, d_psegs, d_ptiles, (int)ptiles.size(), pelems,
                                  d_mask, pstatus, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr, row_mask));
             cur ^= 1;
