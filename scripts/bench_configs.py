@@ -141,6 +141,21 @@ if "cls" in args:
                   "kernels_ms_per_fit": {k: round(v["ms"] / 3, 3) for k, v in prof.items() if v["launches"]},
                   "kernels_alg_gbs": {k: round(v["alg_bytes"] / v["ms"] / 1e6, 1) for k, v in prof.items()
                                       if v["launches"] and v["alg_bytes"] > 0}}
+    if with_cpu:
+        import oracle
+        n_s, f_s = 100_000, min(F, 32)
+        Xc = X[:n_s, :f_s].cpu().numpy()
+        lc = labels[:n_s].cpu().numpy().astype(np.int64)
+        t0 = time.perf_counter()
+        o = oracle.fit_classes(Xc, lc, C, max_depth=10, max_feature=f_s, min_improvement=1e-7,
+                               criterion="p_at_k" if crit is strategy.greedy_classification_p_at_k else "gini")
+        dt = time.perf_counter() - t0
+        g = tree_builder.build_classification_tree(Xc, lc, max_depth=10, max_feature=f_s, min_improvement=1e-7,
+                                                   split_method=crit, max_classes=C)
+        same = all(np.array_equal(getattr(g.tree_, k), getattr(o.tree_, k))
+                   for k in ("children_left", "children_right", "feature", "threshold"))
+        out["cls"]["cpu_port"] = {"sample": f"{n_s} x {f_s}", "fit_s": dt, "rows_features_per_s": n_s * f_s / dt,
+                                  "nodes": o.node_count, "gpu_tree_identical": bool(same)}
     del X, labels
 
 print(json.dumps(out, indent=1))
