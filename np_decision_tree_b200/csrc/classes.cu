@@ -348,7 +348,11 @@ constexpr int STAGE_PITCH = 33;
 // (tile, column, class) as in lookback_count -- instead of the histogram + scan passes.  The grid
 // must be co-resident and tiles are taken in tile-major order (a tile's predecessor has a smaller
 // work index), exactly like the L2 scan (l2.cu).
-template <bool LB>
+//
+// CRIT 1 (precision-at-1): max_c L_c only grows along the chunk (forward pass, stored per position) and
+// max_c R_c only grows when walking the chunk backwards from its end state, so two sweeps over the
+// same counters give max_c L_c(k) + max_c R_c(k) for every position -- no division, integer scores.
+template <bool LB, int CRIT>
 __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__restrict__ orders, int64_t col_stride,
                                                                const CSeg *__restrict__ segs,
                                                                const TileDesc *__restrict__ tiles, int n_tiles, int F,
@@ -357,9 +361,10 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
                                                                CPart *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8;
+    const size_t per_warp = (size_t)(CRIT == 1 ? 2 : 1) * 32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8;
     u64 *pk = reinterpret_cast<u64 *>(smraw + warp * per_warp);             // [C][32] {L (low), R (high)}
     u32 *stage = reinterpret_cast<u32 *>(smraw + warp * per_warp + (size_t)C * 32 * 8);  // [32][33]
+    int *mlbuf = reinterpret_cast<int *>(stage + 32 * STAGE_PITCH);         // CRIT 1: [32][33] max_c L_c per position
     const int64_t total = (int64_t)n_tiles * F;
     for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total; t += (int64_t)gridDim.x * 8) {
         const int f = (int)(t % F), ti = (int)(t / F);
@@ -426,6 +431,7 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
             }
         }
         long long SL = 0, SR = 0;
+        int ml = 0;   // CRIT 1: largest left-hand class count so far
         for (int c = 0; c < C; ++c) {
             int L0;
             if (LB) {
@@ -444,26 +450,57 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
             pk[c * 32 + lane] = (u64)(u32)L0 | ((u64)(u32)R0 << 32);
             SL += (long long)L0 * L0;
             SR += (long long)R0 * R0;
+            ml = max(ml, L0);
         }
         double best = -CUDART_INF;
         int best_k = 0x7fffffff;
-        for (int j = 0; j < mine; ++j) {
-            const int c = (int)(my[j] >> row_bits);
-            const u64 w = pk[c * 32 + lane];
-            const int L = (int)(u32)w, R = (int)(u32)(w >> 32);
-            SL += 2ll * L + 1;
-            SR -= 2ll * R - 1;
-            pk[c * 32 + lane] = (u64)(u32)(L + 1) | ((u64)(u32)(R - 1) << 32);
-            const int kk = off + my0 + j;
-            if (kk < n - 1) {
-                // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
-                const double sc = __dadd_rn(div_counts((double)SL, (double)(kk + 1)),
-                                            div_counts((double)SR, (double)(n - kk - 1)));
-                if (sc > best) {   // positions increase: strict ">" keeps the lowest one
-                    best = sc;
-                    best_k = kk;
+        if (CRIT == 0) {
+            for (int j = 0; j < mine; ++j) {
+                const int c = (int)(my[j] >> row_bits);
+                const u64 w = pk[c * 32 + lane];
+                const int L = (int)(u32)w, R = (int)(u32)(w >> 32);
+                SL += 2ll * L + 1;
+                SR -= 2ll * R - 1;
+                pk[c * 32 + lane] = (u64)(u32)(L + 1) | ((u64)(u32)(R - 1) << 32);
+                const int kk = off + my0 + j;
+                if (kk < n - 1) {
+                    // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
+                    const double sc = __dadd_rn(div_counts((double)SL, (double)(kk + 1)),
+                                                div_counts((double)SR, (double)(n - kk - 1)));
+                    if (sc > best) {   // positions increase: strict ">" keeps the lowest one
+                        best = sc;
+                        best_k = kk;
+                    }
                 }
             }
+        } else {
+            int *myml = mlbuf + lane * STAGE_PITCH;
+            for (int j = 0; j < mine; ++j) {   // forward: the chunk's rows join the left side one by one
+                const int c = (int)(my[j] >> row_bits);
+                const u64 w = pk[c * 32 + lane];
+                const int L = (int)(u32)w + 1, R = (int)(u32)(w >> 32) - 1;
+                ml = max(ml, L);
+                myml[j] = ml;
+                pk[c * 32 + lane] = (u64)(u32)L | ((u64)(u32)R << 32);
+            }
+            int mr = 0;   // largest right-hand class count behind this lane's chunk
+            for (int c = 0; c < C; ++c) mr = max(mr, (int)pk32[(c * 32 + lane) * 2 + 1]);
+            int best_i = -1;
+            for (int j = mine - 1; j >= 0; --j) {   // backward: rows return to the right side
+                const int kk = off + my0 + j;
+                if (kk < n - 1) {
+                    const int sc = myml[j] + mr;   // strategy.py:97-100
+                    if (sc >= best_i) {            // positions decrease: ">=" keeps the lowest one
+                        best_i = sc;
+                        best_k = kk;
+                    }
+                }
+                const int c = (int)(my[j] >> row_bits);
+                const int R = (int)pk32[(c * 32 + lane) * 2 + 1] + 1;
+                pk32[(c * 32 + lane) * 2 + 1] = (u32)R;
+                mr = max(mr, R);
+            }
+            if (best_i >= 0) best = (double)best_i;
         }
         __syncwarp();
 #pragma unroll
@@ -832,7 +869,8 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
 
         const u32 *d_ord = (const u32 *)ord[cur];
         const int64_t work = (int64_t)n_tiles * F;
-        const bool single_pass = criterion == B200DT_GINI && C <= LANE_MAX_CLASSES && !three_pass_env;
+        const bool lane_path = C <= LANE_MAX_CLASSES;
+        const bool single_pass = lane_path && !three_pass_env;
         if (!single_pass) {
             {
                 const size_t smem = (size_t)8 * (C + 1) * 4;
@@ -852,10 +890,13 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
             }
             CK(cudaGetLastError());
         }
-        if (criterion == B200DT_GINI && C <= LANE_MAX_CLASSES) {
-            const size_t smem = (size_t)8 * ((size_t)32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
-            const void *kern = single_pass ? (const void *)class_score_lane_kernel<true>
-                                           : (const void *)class_score_lane_kernel<false>;
+        if (lane_path) {
+            const bool patk = criterion == B200DT_P_AT_1;
+            const size_t smem = (size_t)8 * ((size_t)(patk ? 2 : 1) * 32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
+            const void *kern = patk ? (single_pass ? (const void *)class_score_lane_kernel<true, 1>
+                                                   : (const void *)class_score_lane_kernel<false, 1>)
+                                    : (single_pass ? (const void *)class_score_lane_kernel<true, 0>
+                                                   : (const void *)class_score_lane_kernel<false, 0>);
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = resident_grid(ctx, kern, smem, work);
             u64 *d_status = nullptr;
@@ -873,9 +914,7 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
             if (single_pass)
                 CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));   // tiles wait on earlier tiles
             else
-                class_score_lane_kernel<false><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, Fi,
-                                                                                 C, row_bits, d_excl, d_tot, nullptr, 0u,
-                                                                                 d_part);
+                CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, ctx->stream));
         } else {
             const bool patk = criterion == B200DT_P_AT_1;
             const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;

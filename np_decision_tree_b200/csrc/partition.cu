@@ -96,9 +96,10 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                 if (e < cnt) {
                     const int lb = lb_row + __popc(b & lt);  // left rows before this element
                     const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
-                    ocol[dest] = rows[i];
-                    if (PAY == 1 || PAY == 2) oy[dest] = yv[u];
-                    if (PAY == 2) ow[dest] = wv[u];
+                    // streaming stores: the children are read by the NEXT kernel; keep L1 for the side mask
+                    __stcs(ocol + dest, rows[i]);
+                    if (PAY == 1 || PAY == 2) __stcs(oy + dest, yv[u]);
+                    if (PAY == 2) __stcs(ow + dest, wv[u]);
                 }
                 lb_row += __popc(b);
             }
