@@ -198,6 +198,35 @@ int b200dt_fit_classes(b200dt_ctx *ctx, const double *X, const int32_t *labels, 
                        double min_improvement, int64_t min_sample_leaf, int64_t *children_left,
                        int64_t *children_right, int64_t *feature, double *threshold, double *value,
                        int32_t *n_node_samples, int64_t capacity, int64_t *node_count);
+/* The same fit as a sequence of steps, for feature-sharded multi-GPU fits (one process per GPU,
+ * every rank holds columns [col_offset, col_offset + F_local) of the F_global columns and all labels).
+ * Per level:  search -> all-gather of the candidates -> decide -> sum-all-reduce of the side mask AND of
+ * the left class counts (only the owner of a winning column contributes non-zeros) -> partition.
+ * Candidates carry GLOBAL column ids; every rank takes the same decisions from the same gathered array
+ * (score desc, position asc, column asc = the reference's flat argmax, strategy.py:277-278).
+ * d_left_counts: device int32 [n_live][n_classes] (the first n_split rows are used).
+ * driven by np_decision_tree_b200/sharded.py::fit_classes_sharded. */
+typedef struct b200dt_class_candidate {
+    double score;     /* best surrogate value of the node over this rank's columns            */
+    double threshold; /* feature value at (k, f)                                               */
+    int32_t k;        /* sorted position inside the node, -1 = none                            */
+    int32_t f;        /* GLOBAL column id                                                      */
+    int32_t k_ext;    /* last position whose value equals the threshold (rows go left by value) */
+    int32_t pad;
+} b200dt_class_candidate;
+int b200dt_class_session_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N,
+                               int64_t F_local, int64_t ldx, int space, int n_classes, int criterion,
+                               int max_depth, double min_improvement, int64_t min_sample_leaf,
+                               int64_t col_offset, int64_t F_global);
+int b200dt_class_session_live(b200dt_ctx *ctx, int64_t *n_live);
+int b200dt_class_session_search(b200dt_ctx *ctx, b200dt_class_candidate *d_out);
+int b200dt_class_session_decide(b200dt_ctx *ctx, const b200dt_class_candidate *d_gathered, int n_ranks,
+                                uint32_t *d_side_mask, int32_t *d_left_counts, int64_t *n_split);
+int b200dt_class_session_partition(b200dt_ctx *ctx, const uint32_t *d_side_mask,
+                                   const int32_t *d_left_counts);
+int b200dt_class_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right,
+                                int64_t *feature, double *threshold, double *value,
+                                int32_t *n_node_samples, int64_t capacity, int64_t *node_count);
 /* One node: best (column, sorted position, threshold, surrogate score) over all columns with the
  * reference's flat argmax (lowest position, then lowest column).
  * replaces: strategy.greedy_classification / greedy_classification_p_at_k   ref strategy.py:272-283,313-323 */

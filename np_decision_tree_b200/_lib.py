@@ -32,6 +32,7 @@ class Candidate(ctypes.Structure):
 
 CANDIDATE_BYTES = ctypes.sizeof(Candidate)
 assert CANDIDATE_BYTES == 56
+CLASS_CANDIDATE_BYTES = 32   # b200dt_class_candidate
 
 _SIGNATURES = {
     "b200dt_abi_version": (c_int, []),
@@ -66,6 +67,13 @@ _SIGNATURES = {
                                c_i64, c_vp, c_vp, c_int]),
     "b200dt_fit_classes": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_dbl, c_i64,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
+    "b200dt_class_session_begin": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_dbl,
+                                           c_i64, c_i64, c_i64]),
+    "b200dt_class_session_live": (c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "b200dt_class_session_search": (c_int, [c_vp, c_vp]),
+    "b200dt_class_session_decide": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, ctypes.POINTER(c_i64)]),
+    "b200dt_class_session_partition": (c_int, [c_vp, c_vp, c_vp]),
+    "b200dt_class_session_finish": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "b200dt_class_split_node": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                                         ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl),
                                         ctypes.POINTER(c_dbl)]),

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(256) class_finalize_kernel(const CSeg *__restr
                                                              const CBest *__restrict__ sliced,
                                                              const u32 *__restrict__ orders, int64_t col_stride,
                                                              int row_mask, const double *__restrict__ X, int64_t ldx,
-                                                             CCand *__restrict__ out) {
+                                                             int col_offset, CCand *__restrict__ out) {
     const CSeg sg = segs[blockIdx.x];
     CBest b;
     b.score = -CUDART_INF;
@@ -623,6 +623,7 @@ __global__ void __launch_bounds__(256) class_finalize_kernel(const CSeg *__restr
             }
             c.threshold = thr;
             c.k_ext = lo;
+            c.f += col_offset;   // candidates carry GLOBAL column ids
         } else {
             c.k = -1;
         }
@@ -635,8 +636,8 @@ __global__ void __launch_bounds__(256) class_mark_kernel(const u32 *__restrict__
                                                          const int *__restrict__ marks, int C, int row_bits,
                                                          u32 *mask, int *lcount) {
     extern __shared__ int sh[];
-    const int m = blockIdx.y;
-    const int f = marks[3 * m], start = marks[3 * m + 1], k = marks[3 * m + 2];
+    const int m = blockIdx.y;   // marks: [f_local, start, k, slot of the split node in lcount]
+    const int f = marks[4 * m], start = marks[4 * m + 1], k = marks[4 * m + 2], slot = marks[4 * m + 3];
     for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0;
     __syncthreads();
     const u32 *col = orders + (int64_t)f * col_stride + start;
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(256) class_mark_kernel(const u32 *__restrict__
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256)
-        if (sh[c]) atomicAdd(&lcount[(int64_t)m * C + c], sh[c]);
+        if (sh[c]) atomicAdd(&lcount[(int64_t)slot * C + c], sh[c]);
 }
 
 // numpy's pairwise float64 summation (np.sum of a contiguous 1-D array), for the host-side
@@ -674,13 +675,6 @@ double np_pairwise_sum(const double *a, int64_t n) {
     n2 -= n2 % 8;
     return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
 }
-
-struct CNode {
-    int parent = -1, is_left = 1, depth = 0, start = 0, n = 0;
-    int feature = -2, left = -1, right = -1;
-    double thr = -2.0, value = 0.0;
-    bool leaf = false;
-};
 
 template <typename T>
 int upload_vec(b200dt_ctx *ctx, int pin_slot, size_t pin_off, const std::vector<T> &src, T *dst) {
@@ -714,23 +708,89 @@ int resident_grid(b200dt_ctx *ctx, const void *kern, size_t smem, int64_t work_w
 
 }  // namespace
 
-// Grows the tree (or, with single_node_out set, only searches the root).
-static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F, int64_t ldx,
-                          int space, int C, int criterion, int max_depth, double min_improvement,
-                          int64_t min_sample_leaf, int64_t *children_left, int64_t *children_right,
-                          int64_t *feature, double *threshold, double *value, int32_t *n_node_samples,
-                          int64_t capacity, int64_t *node_count, CCand *single_node_out) {
+// ---------------------------------------------------------------------------------------
+// host side: the level-synchronous classification session
+// ---------------------------------------------------------------------------------------
+struct CNode {
+    int parent = -1, is_left = 1, depth = 0, start = 0, n = 0;
+    int feature = -2, left = -1, right = -1;
+    double thr = -2.0, value = 0.0;
+    bool leaf = false;
+};
+
+
+struct ClassSession {
+    int64_t N = 0, stride = 0, ldx = 0, min_sample_leaf = 1;
+    int F = 0, F_global = 0, col_offset = 0, C = 0, criterion = B200DT_GINI, max_depth = 0;
+    int row_bits = 1, row_mask = 1, cur = 0;
+    double min_improvement = 0.0;
+    bool three_pass = false;     // B200DT_CLASS_3PASS=1: histogram + scan + score passes even where one pass would do
+    bool single_node = false;    // b200dt_class_split_node: the root is searched whatever its size
+    const double *dX = nullptr;
+    int *ord[2] = {nullptr, nullptr};
+    u32 *d_mask = nullptr;       // single-rank fits: the session's own side mask
+    std::vector<CNode> nodes;
+    std::vector<long long> counts;  // counts[node * C + c]
+    std::vector<int> live;
+    // state of the current level
+    std::vector<CSeg> segs;
+    std::vector<TileDesc> tiles;
+    std::vector<int> tot, marks;
+    std::vector<CCand> win;         // winners of the live nodes (after decide)
+    std::vector<int> split_idx;     // indices into live of the nodes that split
+    size_t pin_off = 0;
+    CSeg *d_segs = nullptr;
+
+    bool leaf_by_size(const CNode &nd) const {
+        // base.py:13-21 (rows <= 2 * min_sample_leaf; a one-hot block with a single distinct value: no rows,
+        // or a single class column) and tree_builder.py:74 (depth limit)
+        return (int64_t)nd.n <= 2 * min_sample_leaf || nd.n == 0 || C == 1 || nd.depth >= max_depth;
+    }
+    double first_argmax(int node) const {  // tree_builder.py:20-21: np.argmax of the class counts
+        int best = 0;
+        for (int c = 1; c < C; ++c)
+            if (counts[(size_t)node * C + c] > counts[(size_t)node * C + best]) best = c;
+        return (double)best;
+    }
+};
+
+void class_session_free(b200dt_ctx *ctx) {
+    delete ctx->class_session;
+    ctx->class_session = nullptr;
+}
+
+static int class_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F, int64_t ldx,
+                       int space, int C, int criterion, int max_depth, double min_improvement,
+                       int64_t min_sample_leaf, int64_t col_offset, int64_t F_global, bool single_node) {
     if (N <= 0 || F <= 0) return ctx->fail_msg("fit_classes: empty input");
     if (criterion != B200DT_GINI && criterion != B200DT_P_AT_1) return ctx->fail_msg("fit_classes: unknown criterion");
     if (C < 1 || C > 32 * MAX_CLASS_CHUNKS) return ctx->fail_msg("fit_classes: n_classes must be in [1, 256]");
     if (N > (1ll << 26)) return ctx->fail_msg("fit_classes: N must be <= 2^26 (exact integer class statistics)");
     if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit_classes: max_depth out of range [0, 30]");
+    if (col_offset < 0 || col_offset + F > F_global) return ctx->fail_msg("fit_classes: column slice out of range");
     int row_bits = 1;
     while ((1ll << row_bits) < N) ++row_bits;
     if ((int64_t)C > (1ll << (32 - row_bits)))
         return ctx->fail_msg("fit_classes: n_classes * N does not fit the packed 32-bit (class, row) entries");
-    const int row_mask = (int)((1u << row_bits) - 1u);
-    const int64_t stride = (N + 31) / 32 * 32;
+    class_session_free(ctx);
+    ClassSession *s = new (std::nothrow) ClassSession();
+    if (!s) return ctx->fail_msg("fit_classes: out of host memory");
+    ctx->class_session = s;
+    s->N = N;
+    s->F = (int)F;
+    s->F_global = (int)F_global;
+    s->col_offset = (int)col_offset;
+    s->C = C;
+    s->criterion = criterion;
+    s->max_depth = max_depth;
+    s->min_improvement = min_improvement;
+    s->min_sample_leaf = min_sample_leaf;
+    s->row_bits = row_bits;
+    s->row_mask = (int)((1u << row_bits) - 1u);
+    s->stride = (N + 31) / 32 * 32;
+    s->single_node = single_node;
+    const char *env3 = getenv("B200DT_CLASS_3PASS");
+    s->three_pass = env3 && env3[0] == '1';
 
     // inputs on the device
     const double *dX = X;
@@ -748,6 +808,8 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         dlab = bl;
         dld = F;
     }
+    s->dX = dX;
+    s->ldx = dld;
     // root class totals (+ label range check)
     unsigned long long *d_roothist;
     CKR(scratch_get(ctx, SB_MISC, (size_t)C * 8 + 64, (void **)&d_roothist));
@@ -764,325 +826,354 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
     if ((int)h_root[C] != 0) return ctx->fail_msg("fit_classes: labels must be integers in [0, n_classes)");
 
     // one sort per fit; the class id then joins the row id
-    int *ord[2];
-    CKR(scratch_get(ctx, SB_ORD_A, (size_t)F * stride * 4, (void **)&ord[0]));
-    CKR(scratch_get(ctx, SB_ORD_B, (size_t)F * stride * 4, (void **)&ord[1]));
-    CKR(sort_columns_device(ctx, dX, N, F, dld, ord[0], ord[1], stride));
+    CKR(scratch_get(ctx, SB_ORD_A, (size_t)F * s->stride * 4, (void **)&s->ord[0]));
+    CKR(scratch_get(ctx, SB_ORD_B, (size_t)F * s->stride * 4, (void **)&s->ord[1]));
+    CKR(sort_columns_device(ctx, dX, N, F, dld, s->ord[0], s->ord[1], s->stride));
     {
         LaunchScope ls(ctx, KC_PAYLOAD, 12.0 * (double)N * F);
         pack_labels_kernel<<<dim3((unsigned)std::min<int64_t>(2048, (N + 255) / 256), (unsigned)F), 256, 0, ctx->stream>>>(
-            (u32 *)ord[0], stride, (int)F, N, dlab, row_bits);
+            (u32 *)s->ord[0], s->stride, (int)F, N, dlab, row_bits);
     }
     CK(cudaGetLastError());
-    int cur = 0;
-    u32 *d_mask;
-    CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&d_mask));
+    s->cur = 0;
+    CKR(scratch_get(ctx, SB_MASK, (size_t)((N + 31) / 32) * 4 + 64, (void **)&s->d_mask));
 
-    std::vector<CNode> nodes(1);
-    std::vector<long long> counts(C);  // counts[node * C + c]
-    for (int c = 0; c < C; ++c) counts[c] = (long long)h_root[c];
-    nodes[0].n = (int)N;
-    auto leaf_by_size = [&](const CNode &nd) {
-        // base.py:13-21 (rows <= 2 * min_sample_leaf; a one-hot block with a single distinct value: no rows,
-        // or a single class column) and tree_builder.py:74 (depth limit)
-        return (int64_t)nd.n <= 2 * min_sample_leaf || nd.n == 0 || C == 1 || nd.depth >= max_depth;
-    };
-    auto first_argmax = [&](int node) {  // tree_builder.py:20-21: np.argmax of the class counts
-        int best = 0;
-        for (int c = 1; c < C; ++c)
-            if (counts[(size_t)node * C + c] > counts[(size_t)node * C + best]) best = c;
-        return (double)best;
-    };
-    std::vector<int> live;
-    if (single_node_out == nullptr && leaf_by_size(nodes[0])) {
-        nodes[0].leaf = true;
-        nodes[0].value = first_argmax(0);
+    s->nodes.assign(1, CNode());
+    s->counts.assign(C, 0);
+    for (int c = 0; c < C; ++c) s->counts[c] = (long long)h_root[c];
+    s->nodes[0].n = (int)N;
+    s->live.clear();
+    if (!single_node && s->leaf_by_size(s->nodes[0])) {
+        s->nodes[0].leaf = true;
+        s->nodes[0].value = s->first_argmax(0);
     } else {
-        live.push_back(0);
+        s->live.push_back(0);
     }
+    return 0;
+}
 
-    // B200DT_CLASS_3PASS=1 forces the histogram + scan + score passes (the path of C > 32 and precision-at-1)
-    const char *env3 = getenv("B200DT_CLASS_3PASS");
-    const bool three_pass_env = env3 && env3[0] == '1';
-    std::vector<CSeg> segs;
-    std::vector<TileDesc> tiles;
-    std::vector<int> tot, marks;
-    std::vector<SegDev> psegs;
-    std::vector<TileDesc> ptiles;
-    std::vector<double> frac(C);
-    while (!live.empty()) {
-        const int n_live = (int)live.size();
-        segs.resize(n_live);
-        tiles.clear();
-        tot.resize((size_t)n_live * C);
-        int64_t elems = 0;
-        for (int i = 0; i < n_live; ++i) {
-            const CNode &nd = nodes[live[i]];
-            if (nd.n < 2)
-                return ctx->fail_msg("fit_classes: attempt to split a node with a single row (min_sample_leaf < 1); "
-                                     "the reference raises ValueError here (argmax of an empty sequence)");
-            CSeg sg;
-            sg.start = nd.start;
-            sg.n = nd.n;
-            sg.tile_base = (int)tiles.size();
-            sg.ntiles = (nd.n + GT_TILE - 1) / GT_TILE;
-            sg.st2 = 0;
-            sg.tmax = 0;
-            sg.pad = 0;
-            for (int c = 0; c < C; ++c) {
-                const long long tc = counts[(size_t)live[i] * C + c];
-                tot[(size_t)i * C + c] = (int)tc;
-                sg.st2 += tc * tc;
-                sg.tmax = std::max(sg.tmax, (int)tc);
-            }
-            segs[i] = sg;
-            for (int t = 0; t < sg.ntiles; ++t) tiles.push_back(TileDesc{i, t});
-            elems += nd.n;
+// Search every live node over this rank's columns; one CCand per live node into d_out (device).
+static int class_search(b200dt_ctx *ctx, CCand *d_out) {
+    ClassSession *s = ctx->class_session;
+    if (!s) return ctx->fail_msg("class session: not begun");
+    const int n_live = (int)s->live.size();
+    if (n_live == 0) return 0;
+    const int C = s->C, F = s->F, row_bits = s->row_bits;
+    const int criterion = s->criterion;
+    s->segs.resize(n_live);
+    s->tiles.clear();
+    s->tot.resize((size_t)n_live * C);
+    int64_t elems = 0;
+    for (int i = 0; i < n_live; ++i) {
+        const CNode &nd = s->nodes[s->live[i]];
+        if (nd.n < 2)
+            return ctx->fail_msg("fit_classes: attempt to split a node with a single row (min_sample_leaf < 1); "
+                                 "the reference raises ValueError here (argmax of an empty sequence)");
+        CSeg sg;
+        sg.start = nd.start;
+        sg.n = nd.n;
+        sg.tile_base = (int)s->tiles.size();
+        sg.ntiles = (nd.n + GT_TILE - 1) / GT_TILE;
+        sg.st2 = 0;
+        sg.tmax = 0;
+        sg.pad = 0;
+        for (int c = 0; c < C; ++c) {
+            const long long tc = s->counts[(size_t)s->live[i] * C + c];
+            s->tot[(size_t)i * C + c] = (int)tc;
+            sg.st2 += tc * tc;
+            sg.tmax = std::max(sg.tmax, (int)tc);
         }
-        const int n_tiles = (int)tiles.size();
-        CSeg *d_segs;
-        TileDesc *d_tiles;
-        int *d_tot, *d_hist, *d_excl, *d_rmax;
-        CPart *d_part;
-        CCand *d_cand;
-        const size_t hist_elems = (size_t)n_tiles * F * C;
-        CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(CSeg) + 64, (void **)&d_segs));
-        CKR(scratch_get(ctx, SB_TILES, (size_t)n_tiles * sizeof(TileDesc) + 64, (void **)&d_tiles));
-        CKR(scratch_get(ctx, SB_TMP2, (size_t)n_live * C * 4 + 64, (void **)&d_tot));
+        s->segs[i] = sg;
+        for (int t = 0; t < sg.ntiles; ++t) s->tiles.push_back(TileDesc{i, t});
+        elems += nd.n;
+    }
+    int n_tiles = (int)s->tiles.size();
+    CSeg *d_segs;
+    TileDesc *d_tiles;
+    int *d_tot, *d_hist = nullptr, *d_excl = nullptr, *d_rmax = nullptr;
+    CPart *d_part;
+    const bool lane_path = C <= LANE_MAX_CLASSES;
+    const bool single_pass = lane_path && !s->three_pass;
+    const size_t hist_elems = (size_t)n_tiles * F * C;
+    CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(CSeg) + 64, (void **)&d_segs));
+    CKR(scratch_get(ctx, SB_TILES, (size_t)n_tiles * sizeof(TileDesc) + 64, (void **)&d_tiles));
+    CKR(scratch_get(ctx, SB_TMP2, (size_t)n_live * C * 4 + 64, (void **)&d_tot));
+    if (!single_pass) {
         CKR(scratch_get(ctx, SB_L1_A, hist_elems * 4 + 64, (void **)&d_hist));
         CKR(scratch_get(ctx, SB_L1_B, hist_elems * 4 + 64, (void **)&d_excl));
         CKR(scratch_get(ctx, SB_L1_C, (size_t)n_tiles * F * 4 + 64, (void **)&d_rmax));
-        CKR(scratch_get(ctx, SB_PARTIAL, (size_t)n_tiles * F * sizeof(CPart) + 64, (void **)&d_part));
-        CKR(scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(CCand) + 64, (void **)&d_cand));
-        int64_t stride_arg = stride;   // (non-const copies: their addresses go into a void* launch list)
-        const CSeg *d_segs_c = d_segs;
-        const TileDesc *d_tiles_c = d_tiles;
-        const int *d_excl_c = d_excl, *d_tot_c = d_tot;
-        int n_tiles_arg = n_tiles;
-        size_t po = 0;
-        CKR(upload_vec(ctx, PIN_CLASS, po, segs, d_segs));
-        po += segs.size() * sizeof(CSeg) + 64;
-        CKR(upload_vec(ctx, PIN_CLASS, po, tiles, d_tiles));
-        po += tiles.size() * sizeof(TileDesc) + 64;
-        CKR(upload_vec(ctx, PIN_CLASS, po, tot, d_tot));
-        po += tot.size() * 4 + 64;
-
-        const u32 *d_ord = (const u32 *)ord[cur];
-        const int64_t work = (int64_t)n_tiles * F;
-        const bool lane_path = C <= LANE_MAX_CLASSES;
-        const bool single_pass = lane_path && !three_pass_env;
-        if (!single_pass) {
-            {
-                const size_t smem = (size_t)8 * (C + 1) * 4;
-                const int grid = resident_grid(ctx, (const void *)class_hist_kernel, smem, work);
-                LaunchScope ls(ctx, KC_CLASS_HIST, 4.0 * (double)elems * F);
-                class_hist_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
-                                                                    row_bits, d_hist);
-            }
-            CK(cudaGetLastError());
-            {
-                const int64_t warps = (int64_t)n_live * F;
-                const int grid =
-                    (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16));
-                LaunchScope ls(ctx, KC_MISC, 8.0 * (double)hist_elems);
-                class_scan_kernel<<<grid, 256, 0, ctx->stream>>>(d_segs, n_live, (int)F, C, n_tiles, d_tot, d_hist, d_excl,
-                                                                 criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
-            }
-            CK(cudaGetLastError());
-        }
-        if (lane_path) {
-            const bool patk = criterion == B200DT_P_AT_1;
-            const size_t smem = (size_t)8 * ((size_t)(patk ? 2 : 1) * 32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
-            const void *kern = patk ? (single_pass ? (const void *)class_score_lane_kernel<true, 1>
-                                                   : (const void *)class_score_lane_kernel<false, 1>)
-                                    : (single_pass ? (const void *)class_score_lane_kernel<true, 0>
-                                                   : (const void *)class_score_lane_kernel<false, 0>);
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = resident_grid(ctx, kern, smem, work);
-            u64 *d_status = nullptr;
-            u32 epoch = 0;
-            if (single_pass) {
-                CKR(scratch_get(ctx, SB_STATUS_F, ((size_t)work * C + 1) * 8, (void **)&d_status, true));
-                CKR(class_next_epoch(ctx));
-                epoch = ctx->epoch;
-            }
-            int Fi = (int)F;
-            CPart *d_part_arg = d_part;
-            void *args[] = {&d_ord, &stride_arg, &d_segs_c, &d_tiles_c, &n_tiles_arg, &Fi, &C, &row_bits, &d_excl_c,
-                            &d_tot_c, &d_status, &epoch, &d_part_arg};
-            LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
-            if (single_pass)
-                CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));   // tiles wait on earlier tiles
-            else
-                CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, ctx->stream));
-        } else {
-            const bool patk = criterion == B200DT_P_AT_1;
-            const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;
-            const void *kern = patk ? (const void *)class_score_kernel<1> : (const void *)class_score_kernel<0>;
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = resident_grid(ctx, kern, smem, work);
-            LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
-            if (patk)
-                class_score_kernel<1><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
-                                                                        row_bits, d_excl, d_tot, d_rmax, d_part);
-            else
-                class_score_kernel<0><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, (int)F, C,
-                                                                        row_bits, d_excl, d_tot, d_rmax, d_part);
-        }
-        CK(cudaGetLastError());
-        {
-            CBest *d_sliced;
-            CKR(scratch_get(ctx, SB_L1_G, (size_t)n_live * CF_SLICES * sizeof(CBest) + 64, (void **)&d_sliced));
-            LaunchScope ls(ctx, KC_FINALIZE, (double)work * sizeof(CPart), 2);
-            class_finalize_slices_kernel<<<dim3(n_live, CF_SLICES), 256, 0, ctx->stream>>>(d_segs, (int)F, n_tiles, d_part,
-                                                                                         d_sliced);
-            class_finalize_kernel<<<n_live, 256, 0, ctx->stream>>>(d_segs, d_sliced, d_ord, stride, row_mask, dX, dld,
-                                                                   d_cand);
-        }
-        CK(cudaGetLastError());
-        CCand *h_cand;
-        CKR(pinned_get(ctx, PIN_RESULT, (size_t)n_live * sizeof(CCand), (void **)&h_cand));
-        CK(cudaMemcpyAsync(h_cand, d_cand, (size_t)n_live * sizeof(CCand), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (single_node_out) {
-            *single_node_out = h_cand[0];
-            return 0;
-        }
-
-        // leaf or split (tree_builder.py:83-94)
-        marks.clear();
-        std::vector<int> split_nodes;
-        int max_left = 0;
-        for (int i = 0; i < n_live; ++i) {
-            const int nid = live[i];
-            const CCand &w = h_cand[i];
-            if (w.k < 0) return ctx->fail_msg("fit_classes: a node produced no split candidate");
-            const double nn = (double)nodes[nid].n;
-            double improvement;
-            if (criterion == B200DT_GINI) {
-                for (int c = 0; c < C; ++c) {
-                    const double fr = (double)counts[(size_t)nid * C + c] / nn;
-                    frac[c] = fr * fr;
-                }
-                improvement = w.score / nn - np_pairwise_sum(frac.data(), C);  // strategy.py:107-108
-            } else {
-                improvement = (w.score - (double)segs[i].tmax) / nn;           // strategy.py:103-104
-            }
-            if (improvement < min_improvement) {
-                nodes[nid].leaf = true;
-                nodes[nid].value = first_argmax(nid);
-                continue;
-            }
-            nodes[nid].feature = w.f;
-            nodes[nid].thr = w.threshold;
-            split_nodes.push_back(i);
-            marks.push_back(w.f);
-            marks.push_back(nodes[nid].start);
-            marks.push_back(w.k_ext);
-            max_left = std::max(max_left, w.k_ext + 1);
-        }
-        if (split_nodes.empty()) break;
-        const int n_split = (int)split_nodes.size();
-        int *d_marks, *d_lcount;
-        CKR(scratch_get(ctx, SB_TMP_I64, (size_t)n_split * 12 + 64, (void **)&d_marks));
-        CKR(scratch_get(ctx, SB_L1_D, (size_t)n_split * C * 4 + 64, (void **)&d_lcount));
-        CKR(upload_vec(ctx, PIN_CLASS, po, marks, d_marks));
-        po += marks.size() * 4 + 64;
-        CK(cudaMemsetAsync(d_mask, 0, (size_t)((N + 31) / 32) * 4, ctx->stream));
-        CK(cudaMemsetAsync(d_lcount, 0, (size_t)n_split * C * 4, ctx->stream));
-        {
-            int gx = std::max(1, std::min(2048, (max_left + 255) / 256));
-            for (int m0 = 0; m0 < n_split; m0 += 65535) {
-                const int nm = std::min(65535, n_split - m0);
-                LaunchScope ls(ctx, KC_MARK, 0.0);
-                class_mark_kernel<<<dim3(gx, nm), 256, (size_t)C * 4, ctx->stream>>>(d_ord, stride, d_marks + 3 * m0, C,
-                                                                                   row_bits, d_mask,
-                                                                                   d_lcount + (size_t)m0 * C);
-            }
-        }
-        CK(cudaGetLastError());
-        int *h_lcount;
-        CKR(pinned_get(ctx, PIN_MISC, (size_t)n_split * C * 4, (void **)&h_lcount));
-        CK(cudaMemcpyAsync(h_lcount, d_lcount, (size_t)n_split * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-
-        std::vector<int> next_live;
-        psegs.clear();
-        ptiles.clear();
-        int64_t pelems = 0;
-        for (int j = 0; j < n_split; ++j) {
-            const int i = split_nodes[j], nid = live[i];
-            const int start = nodes[nid].start, n = nodes[nid].n, nl = h_cand[i].k_ext + 1;
-            const int depth = nodes[nid].depth;
-            int child[2];
-            for (int side = 0; side < 2; ++side) {
-                CNode ch;
-                ch.parent = nid;
-                ch.is_left = side == 0;
-                ch.depth = depth + 1;
-                ch.start = side == 0 ? start : start + nl;
-                ch.n = side == 0 ? nl : n - nl;
-                nodes.push_back(ch);
-                child[side] = (int)nodes.size() - 1;
-                counts.resize(nodes.size() * (size_t)C);
-                for (int c = 0; c < C; ++c) {
-                    const long long lc = h_lcount[(size_t)j * C + c];
-                    counts[(size_t)child[side] * C + c] = side == 0 ? lc : counts[(size_t)nid * C + c] - lc;
-                }
-            }
-            nodes[nid].left = child[0];
-            nodes[nid].right = child[1];
-            bool any_search = false;
-            for (int side = 0; side < 2; ++side) {
-                CNode &ch = nodes[child[side]];
-                if (leaf_by_size(ch)) {
-                    ch.leaf = true;
-                    ch.value = first_argmax(child[side]);
-                } else {
-                    next_live.push_back(child[side]);
-                    any_search = true;
-                }
-            }
-            if (any_search) {
-                SegDev sg;
-                sg.total = sg.total_w = 0.0;
-                sg.start = start;
-                sg.n = n;
-                sg.pbase = 0;
-                sg.np = (n + PT_TILE - 1) / PT_TILE;
-                sg.nleft = nl;
-                sg.exact = 0;
-                sg.pstep = 1;
-                sg.pside = 0;
-                const int si = (int)psegs.size();
-                psegs.push_back(sg);
-                for (int t = 0; t < sg.np; ++t) ptiles.push_back(TileDesc{si, t});
-                pelems += n;
-            }
-        }
-        if (!psegs.empty()) {
-            SegDev *d_psegs;
-            TileDesc *d_ptiles;
-            u64 *pstatus;
-            CKR(scratch_get(ctx, SB_PLAN, psegs.size() * sizeof(SegDev) + 64, (void **)&d_psegs));
-            CKR(scratch_get(ctx, SB_TILES, ptiles.size() * sizeof(TileDesc) + 64, (void **)&d_ptiles));
-            CKR(upload_vec(ctx, PIN_CLASS, po, psegs, d_psegs));
-            po += psegs.size() * sizeof(SegDev) + 64;
-            CKR(upload_vec(ctx, PIN_CLASS, po, ptiles, d_ptiles));
-            CKR(scratch_get(ctx, SB_STATUS_P, (ptiles.size() * (size_t)F + 1) * 8, (void **)&pstatus, true));
-            CKR(class_next_epoch(ctx));
-            CKR(launch_partition(ctx, ord[cur], ord[cur ^ 1], stride, (int)F, d_psegs, d_ptiles, (int)ptiles.size(), pelems,
-                                 d_mask, pstatus, ctx->epoch, nullptr, nullptr, nullptr, nullptr, nullptr, row_mask));
-            cur ^= 1;
-            // the pinned staging area is rewritten by the next level: let the copies finish first
-            CK(cudaStreamSynchronize(ctx->stream));
-        }
-        live.swap(next_live);
     }
-    if (single_node_out) return ctx->fail_msg("class_split_node: the node cannot be searched");
+    CKR(scratch_get(ctx, SB_PARTIAL, (size_t)n_tiles * F * sizeof(CPart) + 64, (void **)&d_part));
+    s->d_segs = d_segs;
+    size_t po = 0;
+    CKR(upload_vec(ctx, PIN_CLASS, po, s->segs, d_segs));
+    po += s->segs.size() * sizeof(CSeg) + 64;
+    CKR(upload_vec(ctx, PIN_CLASS, po, s->tiles, d_tiles));
+    po += s->tiles.size() * sizeof(TileDesc) + 64;
+    CKR(upload_vec(ctx, PIN_CLASS, po, s->tot, d_tot));
+    po += s->tot.size() * 4 + 64;
+    s->pin_off = po;
 
+    const u32 *d_ord = (const u32 *)s->ord[s->cur];
+    int64_t stride = s->stride;
+    const int64_t work = (int64_t)n_tiles * F;
+    if (!single_pass) {
+        {
+            const size_t smem = (size_t)8 * (C + 1) * 4;
+            const int grid = resident_grid(ctx, (const void *)class_hist_kernel, smem, work);
+            LaunchScope ls(ctx, KC_CLASS_HIST, 4.0 * (double)elems * F);
+            class_hist_kernel<<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, F, C, row_bits,
+                                                                d_hist);
+        }
+        CK(cudaGetLastError());
+        {
+            const int64_t warps = (int64_t)n_live * F;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16));
+            LaunchScope ls(ctx, KC_MISC, 8.0 * (double)hist_elems);
+            class_scan_kernel<<<grid, 256, 0, ctx->stream>>>(d_segs, n_live, F, C, n_tiles, d_tot, d_hist, d_excl,
+                                                             criterion == B200DT_P_AT_1 ? d_rmax : nullptr);
+        }
+        CK(cudaGetLastError());
+    }
+    if (lane_path) {
+        const bool patk = criterion == B200DT_P_AT_1;
+        const size_t smem = (size_t)8 * ((size_t)(patk ? 2 : 1) * 32 * STAGE_PITCH * 4 + (size_t)C * 32 * 8);
+        const void *kern = patk ? (single_pass ? (const void *)class_score_lane_kernel<true, 1>
+                                               : (const void *)class_score_lane_kernel<false, 1>)
+                                : (single_pass ? (const void *)class_score_lane_kernel<true, 0>
+                                               : (const void *)class_score_lane_kernel<false, 0>);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = resident_grid(ctx, kern, smem, work);
+        u64 *d_status = nullptr;
+        u32 epoch = 0;
+        if (single_pass) {
+            CKR(scratch_get(ctx, SB_STATUS_F, ((size_t)work * C + 1) * 8, (void **)&d_status, true));
+            CKR(class_next_epoch(ctx));
+            epoch = ctx->epoch;
+        }
+        const CSeg *a_segs = d_segs;
+        const TileDesc *a_tiles = d_tiles;
+        const int *a_excl = d_excl, *a_tot = d_tot;
+        int a_F = F, a_C = C, a_bits = row_bits;
+        void *args[] = {&d_ord, &stride, &a_segs, &a_tiles, &n_tiles, &a_F, &a_C, &a_bits, &a_excl, &a_tot, &d_status,
+                        &epoch, &d_part};
+        LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
+        if (single_pass)
+            CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));   // tiles wait on earlier tiles
+        else
+            CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, ctx->stream));
+    } else {
+        const bool patk = criterion == B200DT_P_AT_1;
+        const size_t smem = (size_t)8 * (2 * (C + 1) + (patk ? 2 * GT_TILE : 0)) * 4;
+        const void *kern = patk ? (const void *)class_score_kernel<1> : (const void *)class_score_kernel<0>;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = resident_grid(ctx, kern, smem, work);
+        LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
+        if (patk)
+            class_score_kernel<1><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, F, C, row_bits,
+                                                                    d_excl, d_tot, d_rmax, d_part);
+        else
+            class_score_kernel<0><<<grid, 256, smem, ctx->stream>>>(d_ord, stride, d_segs, d_tiles, n_tiles, F, C, row_bits,
+                                                                    d_excl, d_tot, d_rmax, d_part);
+    }
+    CK(cudaGetLastError());
+    {
+        CBest *d_sliced;
+        CKR(scratch_get(ctx, SB_L1_G, (size_t)n_live * CF_SLICES * sizeof(CBest) + 64, (void **)&d_sliced));
+        LaunchScope ls(ctx, KC_FINALIZE, (double)work * sizeof(CPart), 2);
+        class_finalize_slices_kernel<<<dim3(n_live, CF_SLICES), 256, 0, ctx->stream>>>(d_segs, F, n_tiles, d_part, d_sliced);
+        class_finalize_kernel<<<n_live, 256, 0, ctx->stream>>>(d_segs, d_sliced, d_ord, stride, s->row_mask, s->dX, s->ldx,
+                                                               s->col_offset, d_out);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Pick the winner of every live node among the ranks' candidates ([rank][node] records), apply the leaf
+// test, and -- for the winning columns this rank owns -- set the left rows' bits in d_mask and count
+// their classes into d_lcount ([split node][class]; zero where another rank owns the column).
+static int class_decide(b200dt_ctx *ctx, const CCand *d_gathered, int n_ranks, u32 *d_mask, int *d_lcount,
+                        int64_t *n_split_out) {
+    ClassSession *s = ctx->class_session;
+    if (!s) return ctx->fail_msg("class session: not begun");
+    *n_split_out = 0;
+    const int n_live = (int)s->live.size();
+    if (n_live == 0) return 0;
+    const int C = s->C;
+    CCand *h;
+    CKR(pinned_get(ctx, PIN_RESULT, (size_t)n_ranks * n_live * sizeof(CCand), (void **)&h));
+    CK(cudaMemcpyAsync(h, d_gathered, (size_t)n_ranks * n_live * sizeof(CCand), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    s->win.resize(n_live);
+    s->split_idx.clear();
+    s->marks.clear();
+    std::vector<double> frac(C);
+    int max_left = 0, n_owned = 0;
+    for (int i = 0; i < n_live; ++i) {
+        // flat argmax over (position, GLOBAL column): strategy.py:277-278
+        CCand w = h[i];
+        for (int r = 1; r < n_ranks; ++r) {
+            const CCand &c = h[(size_t)r * n_live + i];
+            if (c.k < 0) continue;
+            if (w.k < 0 || c.score > w.score || (c.score == w.score && (c.k < w.k || (c.k == w.k && c.f < w.f)))) w = c;
+        }
+        if (w.k < 0) return ctx->fail_msg("fit_classes: a node produced no split candidate");
+        s->win[i] = w;
+        const int nid = s->live[i];
+        const double nn = (double)s->nodes[nid].n;
+        double improvement;
+        if (s->criterion == B200DT_GINI) {
+            for (int c = 0; c < C; ++c) {
+                const double fr = (double)s->counts[(size_t)nid * C + c] / nn;
+                frac[c] = fr * fr;
+            }
+            improvement = w.score / nn - np_pairwise_sum(frac.data(), C);  // strategy.py:107-108
+        } else {
+            improvement = (w.score - (double)s->segs[i].tmax) / nn;        // strategy.py:103-104
+        }
+        if (improvement < s->min_improvement) {   // tree_builder.py:83-84
+            s->nodes[nid].leaf = true;
+            s->nodes[nid].value = s->first_argmax(nid);
+            continue;
+        }
+        s->nodes[nid].feature = w.f;
+        s->nodes[nid].thr = w.threshold;
+        const int slot = (int)s->split_idx.size();
+        s->split_idx.push_back(i);
+        const int fl = w.f - s->col_offset;
+        if (fl >= 0 && fl < s->F) {   // this rank owns the winning column
+            s->marks.push_back(fl);
+            s->marks.push_back(s->nodes[nid].start);
+            s->marks.push_back(w.k_ext);
+            s->marks.push_back(slot);
+            max_left = std::max(max_left, w.k_ext + 1);
+            ++n_owned;
+        }
+    }
+    const int n_split = (int)s->split_idx.size();
+    *n_split_out = n_split;
+    if (n_split == 0) {
+        s->live.clear();
+        return 0;
+    }
+    CK(cudaMemsetAsync(d_mask, 0, (size_t)((s->N + 31) / 32) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_lcount, 0, (size_t)n_split * C * 4, ctx->stream));
+    if (n_owned > 0) {
+        int *d_marks;
+        CKR(scratch_get(ctx, SB_TMP_I64, (size_t)n_owned * 16 + 64, (void **)&d_marks));
+        CKR(upload_vec(ctx, PIN_CLASS, s->pin_off, s->marks, d_marks));
+        s->pin_off += s->marks.size() * 4 + 64;
+        const int gx = std::max(1, std::min(2048, (max_left + 255) / 256));
+        for (int m0 = 0; m0 < n_owned; m0 += 65535) {
+            const int nm = std::min(65535, n_owned - m0);
+            LaunchScope ls(ctx, KC_MARK, 0.0);
+            class_mark_kernel<<<dim3(gx, nm), 256, (size_t)C * 4, ctx->stream>>>(
+                (const u32 *)s->ord[s->cur], s->stride, d_marks + 4 * m0, C, s->row_bits, d_mask, d_lcount);
+        }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// Children of the split nodes from the (all-reduced) left class counts, then the stable partition.
+static int class_partition(b200dt_ctx *ctx, const u32 *d_mask, const int *d_lcount) {
+    ClassSession *s = ctx->class_session;
+    if (!s) return ctx->fail_msg("class session: not begun");
+    const int n_split = (int)s->split_idx.size();
+    if (n_split == 0) return 0;
+    const int C = s->C;
+    int *h_lcount;
+    CKR(pinned_get(ctx, PIN_MISC, (size_t)n_split * C * 4, (void **)&h_lcount));
+    CK(cudaMemcpyAsync(h_lcount, d_lcount, (size_t)n_split * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> next_live;
+    std::vector<SegDev> psegs;
+    std::vector<TileDesc> ptiles;
+    int64_t pelems = 0;
+    for (int j = 0; j < n_split; ++j) {
+        const int i = s->split_idx[j], nid = s->live[i];
+        const int start = s->nodes[nid].start, n = s->nodes[nid].n, nl = s->win[i].k_ext + 1;
+        const int depth = s->nodes[nid].depth;
+        long long lsum = 0;
+        for (int c = 0; c < C; ++c) lsum += h_lcount[(size_t)j * C + c];
+        if (lsum != nl) return ctx->fail_msg("fit_classes: left class counts do not add up (mask / count exchange)");
+        int child[2];
+        for (int side = 0; side < 2; ++side) {
+            CNode ch;
+            ch.parent = nid;
+            ch.is_left = side == 0;
+            ch.depth = depth + 1;
+            ch.start = side == 0 ? start : start + nl;
+            ch.n = side == 0 ? nl : n - nl;
+            s->nodes.push_back(ch);
+            child[side] = (int)s->nodes.size() - 1;
+            s->counts.resize(s->nodes.size() * (size_t)C);
+            for (int c = 0; c < C; ++c) {
+                const long long lc = h_lcount[(size_t)j * C + c];
+                s->counts[(size_t)child[side] * C + c] = side == 0 ? lc : s->counts[(size_t)nid * C + c] - lc;
+            }
+        }
+        s->nodes[nid].left = child[0];
+        s->nodes[nid].right = child[1];
+        bool any_search = false;
+        for (int side = 0; side < 2; ++side) {
+            CNode &ch = s->nodes[child[side]];
+            if (s->leaf_by_size(ch)) {
+                ch.leaf = true;
+                ch.value = s->first_argmax(child[side]);
+            } else {
+                next_live.push_back(child[side]);
+                any_search = true;
+            }
+        }
+        if (any_search) {
+            SegDev sg;
+            sg.total = sg.total_w = 0.0;
+            sg.start = start;
+            sg.n = n;
+            sg.pbase = 0;
+            sg.np = (n + PT_TILE - 1) / PT_TILE;
+            sg.nleft = nl;
+            sg.exact = 0;
+            sg.pstep = 1;
+            sg.pside = 0;
+            const int si = (int)psegs.size();
+            psegs.push_back(sg);
+            for (int t = 0; t < sg.np; ++t) ptiles.push_back(TileDesc{si, t});
+            pelems += n;
+        }
+    }
+    if (!psegs.empty()) {
+        SegDev *d_psegs;
+        TileDesc *d_ptiles;
+        u64 *pstatus;
+        CKR(scratch_get(ctx, SB_PLAN, psegs.size() * sizeof(SegDev) + 64, (void **)&d_psegs));
+        CKR(scratch_get(ctx, SB_TILES, ptiles.size() * sizeof(TileDesc) + 64, (void **)&d_ptiles));
+        CKR(upload_vec(ctx, PIN_CLASS, s->pin_off, psegs, d_psegs));
+        s->pin_off += psegs.size() * sizeof(SegDev) + 64;
+        CKR(upload_vec(ctx, PIN_CLASS, s->pin_off, ptiles, d_ptiles));
+        CKR(scratch_get(ctx, SB_STATUS_P, (ptiles.size() * (size_t)s->F + 1) * 8, (void **)&pstatus, true));
+        CKR(class_next_epoch(ctx));
+        CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->stride, s->F, d_psegs, d_ptiles,
+                             (int)ptiles.size(), pelems, d_mask, pstatus, ctx->epoch, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, s->row_mask));
+        s->cur ^= 1;
+        // the pinned staging area is rewritten by the next level: let the copies finish first
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    s->live.swap(next_live);
+    s->split_idx.clear();
+    return 0;
+}
+
+static int class_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
+                        double *threshold, double *value, int32_t *n_node_samples, int64_t capacity,
+                        int64_t *node_count) {
+    ClassSession *s = ctx->class_session;
+    if (!s) return ctx->fail_msg("class session: not begun");
+    if (!s->live.empty()) return ctx->fail_msg("class session: finish called before the tree is complete");
     // pre-order ids, left first (base.py:47-52; tree_builder.py:91-94 pushes right, then left)
-    const int64_t count = (int64_t)nodes.size();
+    const int64_t count = (int64_t)s->nodes.size();
     if (count > capacity) return ctx->fail_msg("fit_classes: tree arrays too small");
     std::vector<int> new_id(count, -1), stack(1, 0);
     int next = 0;
@@ -1090,13 +1181,13 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         const int v = stack.back();
         stack.pop_back();
         new_id[v] = next++;
-        if (!nodes[v].leaf) {
-            stack.push_back(nodes[v].right);
-            stack.push_back(nodes[v].left);
+        if (!s->nodes[v].leaf) {
+            stack.push_back(s->nodes[v].right);
+            stack.push_back(s->nodes[v].left);
         }
     }
     for (int64_t v = 0; v < count; ++v) {
-        const CNode &nd = nodes[v];
+        const CNode &nd = s->nodes[v];
         const int id = new_id[v];
         if (nd.leaf) {
             children_left[id] = -1;
@@ -1114,10 +1205,61 @@ static int class_fit_impl(b200dt_ctx *ctx, const double *X, const int32_t *label
         if (n_node_samples) n_node_samples[id] = nd.n;
     }
     *node_count = count;
+    class_session_free(ctx);
     return 0;
 }
 
+static_assert(sizeof(CCand) == sizeof(b200dt_class_candidate), "candidate layout");
+
 extern "C" {
+
+int b200dt_class_session_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F_local,
+                               int64_t ldx, int space, int n_classes, int criterion, int max_depth,
+                               double min_improvement, int64_t min_sample_leaf, int64_t col_offset, int64_t F_global) {
+    if (!ctx) return 1;
+    if (!X || !labels) return ctx->fail_msg("class_session_begin: null argument");
+    CK(cudaSetDevice(ctx->device));
+    return class_begin(ctx, X, labels, N, F_local, ldx, space, n_classes, criterion, max_depth, min_improvement,
+                       min_sample_leaf, col_offset, F_global, false);
+}
+
+int b200dt_class_session_live(b200dt_ctx *ctx, int64_t *n_live) {
+    if (!ctx) return 1;
+    if (!ctx->class_session) return ctx->fail_msg("class session: not begun");
+    *n_live = (int64_t)ctx->class_session->live.size();
+    return 0;
+}
+
+int b200dt_class_session_search(b200dt_ctx *ctx, b200dt_class_candidate *d_out) {
+    if (!ctx) return 1;
+    CK(cudaSetDevice(ctx->device));
+    return class_search(ctx, reinterpret_cast<CCand *>(d_out));
+}
+
+int b200dt_class_session_decide(b200dt_ctx *ctx, const b200dt_class_candidate *d_gathered, int n_ranks,
+                                uint32_t *d_side_mask, int32_t *d_left_counts, int64_t *n_split) {
+    if (!ctx) return 1;
+    if (!d_gathered || !d_side_mask || !d_left_counts || !n_split || n_ranks < 1)
+        return ctx->fail_msg("class_session_decide: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    return class_decide(ctx, reinterpret_cast<const CCand *>(d_gathered), n_ranks, d_side_mask, d_left_counts, n_split);
+}
+
+int b200dt_class_session_partition(b200dt_ctx *ctx, const uint32_t *d_side_mask, const int32_t *d_left_counts) {
+    if (!ctx) return 1;
+    CK(cudaSetDevice(ctx->device));
+    return class_partition(ctx, d_side_mask, d_left_counts);
+}
+
+int b200dt_class_session_finish(b200dt_ctx *ctx, int64_t *children_left, int64_t *children_right, int64_t *feature,
+                                double *threshold, double *value, int32_t *n_node_samples, int64_t capacity,
+                                int64_t *node_count) {
+    if (!ctx) return 1;
+    if (!children_left || !children_right || !feature || !threshold || !value || !node_count)
+        return ctx->fail_msg("class_session_finish: null argument");
+    return class_finish(ctx, children_left, children_right, feature, threshold, value, n_node_samples, capacity,
+                        node_count);
+}
 
 int b200dt_fit_classes(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F, int64_t ldx,
                        int space, int n_classes, int criterion, int max_depth, double min_improvement,
@@ -1128,9 +1270,25 @@ int b200dt_fit_classes(b200dt_ctx *ctx, const double *X, const int32_t *labels, 
     if (!X || !labels || !children_left || !children_right || !feature || !threshold || !value || !node_count)
         return ctx->fail_msg("fit_classes: null argument");
     CK(cudaSetDevice(ctx->device));
-    return class_fit_impl(ctx, X, labels, N, F, ldx, space, n_classes, criterion, max_depth, min_improvement,
-                          min_sample_leaf, children_left, children_right, feature, threshold, value, n_node_samples,
-                          capacity, node_count, nullptr);
+    int r = class_begin(ctx, X, labels, N, F, ldx, space, n_classes, criterion, max_depth, min_improvement,
+                        min_sample_leaf, 0, F, false);
+    while (r == 0 && !ctx->class_session->live.empty()) {
+        ClassSession *s = ctx->class_session;
+        const int n_live = (int)s->live.size();
+        CCand *d_cand;
+        int *d_lcount;
+        int64_t n_split = 0;
+        r = scratch_get(ctx, SB_RESULT, (size_t)n_live * sizeof(CCand) + 64, (void **)&d_cand);
+        if (r == 0) r = scratch_get(ctx, SB_L1_D, (size_t)n_live * n_classes * 4 + 64, (void **)&d_lcount);
+        if (r == 0) r = class_search(ctx, d_cand);
+        if (r == 0) r = class_decide(ctx, d_cand, 1, s->d_mask, d_lcount, &n_split);
+        if (r == 0) r = class_partition(ctx, s->d_mask, d_lcount);
+    }
+    if (r == 0)
+        r = class_finish(ctx, children_left, children_right, feature, threshold, value, n_node_samples, capacity,
+                         node_count);
+    class_session_free(ctx);
+    return r;
 }
 
 int b200dt_class_split_node(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t n, int64_t F, int64_t ldx,
@@ -1141,10 +1299,20 @@ int b200dt_class_split_node(b200dt_ctx *ctx, const double *X, const int32_t *lab
         return ctx->fail_msg("class_split_node: null argument");
     if (n < 2) return ctx->fail_msg("class_split_node: attempt to get argmax of an empty sequence (n < 2)");
     CK(cudaSetDevice(ctx->device));
+    int r = class_begin(ctx, X, labels, n, F, ldx, space, n_classes, criterion, 1, 0.0, 0, 0, F, true);
     CCand c;
-    int64_t dummy = 0;
-    CKR(class_fit_impl(ctx, X, labels, n, F, ldx, space, n_classes, criterion, 1, 0.0, 0, nullptr, nullptr, nullptr,
-                       nullptr, nullptr, nullptr, 0, &dummy, &c));
+    if (r == 0) {
+        CCand *d_cand;
+        r = scratch_get(ctx, SB_RESULT, sizeof(CCand) + 64, (void **)&d_cand);
+        if (r == 0) r = class_search(ctx, d_cand);
+        if (r == 0) {
+            CK(cudaMemcpyAsync(&c, d_cand, sizeof(CCand), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    class_session_free(ctx);
+    if (r) return r;
+    if (c.k < 0) return ctx->fail_msg("class_split_node: the node cannot be searched");
     *out_f = c.f;
     *out_k = c.k;
     *out_threshold = c.threshold;

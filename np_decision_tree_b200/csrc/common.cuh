@@ -54,7 +54,8 @@ struct ProfSlot {
     int kc;
 };
 
-struct Session;  // fit.cu
+struct Session;       // fit.cu
+struct ClassSession;  // classes.cu
 
 struct b200dt_ctx {
     int device = 0;
@@ -83,6 +84,7 @@ struct b200dt_ctx {
     std::vector<size_t> pinned_cap;
 
     Session *session = nullptr;
+    ClassSession *class_session = nullptr;
 
     int fail(const char *what, cudaError_t e, const char *file, int line) {
         char buf[512];

@@ -122,6 +122,60 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
     return tree
 
 
+def fit_classes_sharded(X_local, labels, col_offset, n_features, n_classes, criterion=_lib.GINI, max_depth=2,
+                        min_improvement=0.01, min_sample_leaf=1, group=None, ctx=None):
+    """Grow one classification tree (exhaustive gini / precision-at-1 search, ref
+    decision_tree/tree_builder.py:56-96,149-159) over columns sharded across the ranks of ``group``.
+
+    X_local: (N, F_local) float64 CUDA tensor -- this rank's columns [col_offset, col_offset + F_local).
+    labels:  (N,) int32 CUDA tensor of class ids in [0, n_classes), replicated.
+    Per level: all-gather of one 32-byte candidate per live node, then a sum-all-reduce of the N-bit
+    left-row mask and of the left children's class counts (both written only by the owner of the
+    winning column).  Returns a base.DecisionTree identical on every rank and to the 1-GPU tree.
+    """
+    import torch
+    import torch.distributed as dist
+    from .decision_tree.base import DecisionTree as ClassTree
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if not (X_local.is_cuda and labels.is_cuda):
+        raise TypeError("fit_classes_sharded takes CUDA tensors")
+    dev = X_local.device
+    ctx = ctx or _lib.default_context(dev.index)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    X_local = X_local.contiguous()
+    labels = labels.to(torch.int32).contiguous()
+    N, F_local = X_local.shape
+    lib, h = ctx.lib, ctx.handle
+    ctx.check(lib.b200dt_class_session_begin(h, X_local.data_ptr(), labels.data_ptr(), N, F_local, X_local.stride(0),
+                                             _lib.DEVICE, int(n_classes), int(criterion), int(max_depth),
+                                             float(min_improvement), int(min_sample_leaf), int(col_offset),
+                                             int(n_features)))
+    mask = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
+    n_live, n_split = ctypes.c_int64(), ctypes.c_int64()
+    while True:
+        ctx.check(lib.b200dt_class_session_live(h, ctypes.byref(n_live)))
+        if n_live.value == 0:
+            break
+        cand = torch.empty(n_live.value * _lib.CLASS_CANDIDATE_BYTES, dtype=torch.uint8, device=dev)
+        left_counts = torch.zeros(n_live.value * int(n_classes), dtype=torch.int32, device=dev)
+        ctx.check(lib.b200dt_class_session_search(h, cand.data_ptr()))
+        gathered = gather_candidates(cand, world, group)
+        ctx.check(lib.b200dt_class_session_decide(h, gathered.data_ptr(), world, mask.data_ptr(),
+                                                  left_counts.data_ptr(), ctypes.byref(n_split)))
+        if n_split.value:
+            reduce_side_mask(mask, world, group)
+            reduce_side_mask(left_counts, world, group)
+            ctx.check(lib.b200dt_class_session_partition(h, mask.data_ptr(), left_counts.data_ptr()))
+    tree = ClassTree(2 ** (max_depth + 1))
+    t = tree.tree_
+    count = ctypes.c_int64()
+    ctx.check(lib.b200dt_class_session_finish(h, t.children_left.ctypes.data, t.children_right.ctypes.data,
+                                              t.feature.ctypes.data, t.threshold.ctypes.data, t.value.ctypes.data,
+                                              None, t.feature.shape[0], ctypes.byref(count)))
+    tree.max_node_ = int(count.value) - 1
+    return tree
+
+
 def predict_sharded_rows(X_rows, tree, ctx=None):
     """Inference shards by rows with no exchange: each rank predicts its own rows."""
     from .decision_tree.utils import inference

@@ -88,3 +88,52 @@ def test_world1_is_a_no_op():
     assert gather_candidates(buf, 1) is buf
     m = torch.ones(4, dtype=torch.int32)
     assert reduce_side_mask(m, 1) is m
+
+
+# ---- classification sessions: 32-byte candidates, and the left class counts travel like the mask ----
+def _class_candidates(rank, world, n_cols=9):
+    rec = np.zeros(N_NODES, dtype=[("score", "f8"), ("threshold", "f8"), ("k", "i4"), ("f", "i4"), ("k_ext", "i4"),
+                                   ("pad", "i4")])
+    assert rec.itemsize == _lib.CLASS_CANDIDATE_BYTES
+    lo, hi = shard_columns(n_cols, world, rank)
+    for node in range(N_NODES):
+        k = (node + rank) % 3
+        rec[node] = (float((node * 5 + rank * 2) % 4), 0.5 * rank, k, lo + node % (hi - lo), k + node % 2, 0)
+    return rec
+
+
+def _class_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_classes = 3
+        mine = _class_candidates(rank, world)
+        buf = torch.from_numpy(mine.view(np.uint8).copy())
+        gathered = gather_candidates(buf, world).numpy().view(mine.dtype).reshape(world, N_NODES)
+        for r in range(world):
+            assert np.array_equal(gathered[r], _class_candidates(r, world))
+        # flat argmax over (position, GLOBAL column): score desc, k asc, f asc (ref strategy.py:277-278)
+        winners = [min(range(world), key=lambda r: (-gathered[r][node]["score"], gathered[r][node]["k"],
+                                                    gathered[r][node]["f"])) for node in range(N_NODES)]
+        # only the owner of a winning column knows the left child's class counts; the others send zeros
+        counts = torch.zeros(N_NODES * n_classes, dtype=torch.int32)
+        expect = np.zeros((N_NODES, n_classes), dtype=np.int32)
+        for node, w in enumerate(winners):
+            expect[node] = [node + 1, 2 * node, gathered[w][node]["k_ext"]]
+            if w == rank:
+                counts.view(N_NODES, n_classes)[node] = torch.from_numpy(expect[node])
+        reduce_side_mask(counts, world)
+        assert np.array_equal(counts.numpy().reshape(N_NODES, n_classes), expect)
+        out[rank] = winners
+    finally:
+        dist.destroy_process_group()
+
+
+def test_class_exchange_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_class_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0] == out[1] and len(out[0]) == N_NODES
