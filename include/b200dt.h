@@ -234,6 +234,28 @@ int b200dt_class_split_node(b200dt_ctx *ctx, const double *X, const int32_t *lab
                             int64_t ldx, int space, int n_classes, int criterion, int64_t *out_f,
                             int64_t *out_k, double *out_threshold, double *out_score);
 
+/* ---- K7: node-at-a-time primitives for the random-threshold classification splitters -----------
+ * replaces the array work of strategy.random_classify / random_classify_p_at_k (ref strategy.py:149-172)
+ * under tree_builder.build_tree (ref tree_builder.py:24-41,43-52,56-96).  The reference draws its thresholds
+ * (and its column sub-samples) from numpy's GLOBAL generator per node in depth-first order, so the host keeps
+ * that loop and those np.random calls; per node the GPU supplies
+ *   minmax:            np.min / np.max over the node's rows of the given columns        (strategy.py:150)
+ *   threshold_counts:  class counts of the rows with x <= threshold, per column         (strategy.py:151-153)
+ *   split:             stable split of the node's row list by (column, threshold)       (tree_builder.py:31-34)
+ * A node is the segment [start, start + n) of row-id array `buffer` (0 / 1); `split` writes the children into
+ * the same segment of the other array: left rows [start, start + n_left), right rows behind them.  The root is
+ * segment [0, N) of buffer 0.  cols / thresholds / outputs are HOST arrays; out_counts is [n_cols][n_classes]. */
+int b200dt_rows_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, int64_t N, int64_t F,
+                      int64_t ldx, int space, int n_classes, int64_t *class_counts);
+int b200dt_rows_minmax(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, const int32_t *cols,
+                       int n_cols, double *out_min, double *out_max);
+int b200dt_rows_threshold_counts(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n,
+                                 const int32_t *cols, int n_cols, const double *thresholds,
+                                 int64_t *out_counts);
+int b200dt_rows_split(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, int32_t col,
+                      double threshold, int64_t *n_left);
+int b200dt_rows_end(b200dt_ctx *ctx);
+
 /* ---- measurement -------------------------------------------------------------------
  * When enabled, every kernel launch is bracketed by CUDA events on the launch stream;
  * `get` synchronises and returns, per kernel class, the summed device time, the number of

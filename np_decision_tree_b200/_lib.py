@@ -77,6 +77,11 @@ _SIGNATURES = {
     "b200dt_class_split_node": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                                         ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl),
                                         ctypes.POINTER(c_dbl)]),
+    "b200dt_rows_begin": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
+    "b200dt_rows_minmax": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
+    "b200dt_rows_threshold_counts": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
+    "b200dt_rows_split": (c_int, [c_vp, c_int, c_i64, c_i64, ctypes.c_int32, c_dbl, ctypes.POINTER(c_i64)]),
+    "b200dt_rows_end": (c_int, [c_vp]),
     "b200dt_profile_enable": (c_int, [c_vp, c_int]),
     "b200dt_profile_reset": (c_int, [c_vp]),
     "b200dt_profile_count": (c_int, []),

@@ -35,6 +35,7 @@ enum KernelClass {
     KC_SORT_FIXUP,        // 32-bit sort path: gather full keys, repair runs tied on the top 32 bits
     KC_CLASS_HIST,        // classification: per-tile class histograms
     KC_CLASS_SCORE,       // classification: gini / precision-at-1 scores + argmax
+    KC_ROWS,              // random-threshold splitters: column min/max, threshold counts, row-list split
     KC_COUNT
 };
 
@@ -42,7 +43,7 @@ static const char *const kKernelClassNames[KC_COUNT] = {
     "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
     "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
     "misc", "level_fused_partition_search", "gather_y_payload", "sort_fixup_ties", "class_tile_histogram",
-    "class_score_search"};
+    "class_score_search", "row_list_ops"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -56,6 +57,7 @@ struct ProfSlot {
 
 struct Session;       // fit.cu
 struct ClassSession;  // classes.cu
+struct RowSession;    // rows.cu
 
 struct b200dt_ctx {
     int device = 0;
@@ -85,6 +87,7 @@ struct b200dt_ctx {
 
     Session *session = nullptr;
     ClassSession *class_session = nullptr;
+    RowSession *row_session = nullptr;
 
     int fail(const char *what, cudaError_t e, const char *file, int line) {
         char buf[512];

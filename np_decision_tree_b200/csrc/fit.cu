@@ -782,6 +782,7 @@ void b200dt_destroy(b200dt_ctx *ctx) {
     prof_drain(ctx);
     session_free(ctx);
     class_session_free(ctx);
+    row_session_free(ctx);
     for (auto &b : ctx->scratch)
         if (b.p) cudaFree(b.p);
     for (auto p : ctx->pinned)

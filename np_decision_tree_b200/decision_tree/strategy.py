@@ -7,8 +7,11 @@ precision-at-1 surrogate of every split position, flat argmax -- runs on the GPU
 (``b200dt_class_split_node``, csrc/classes.cu).  Citations are to
 /root/reference/decision_tree/strategy.py.
 
-The random-threshold splitters (``random_classify`` ..., strategy.py:136-185) draw from
-``np.random`` per node and are not part of the accelerated path.
+``random_classify`` / ``random_classify_p_at_k`` (strategy.py:149-172) draw one threshold per column
+from numpy's GLOBAL generator; the draw stays on the host (same ``np.random.uniform`` call, so a seeded
+run reproduces the reference), the column min / max and the class counts left of the thresholds come
+from the GPU (csrc/rows.cu).  The regression-side random splitters (``random_split``,
+``random_split_v2``) are not accelerated.
 """
 import ctypes
 
@@ -26,6 +29,35 @@ def surrogate_to_p_at_k(value, y):
 def surrogate_to_gini(value, y):
     """strategy.py:107-108."""
     return value / y.shape[0] - np.sum(np.square(y.sum(axis=0) / y.sum()))
+
+
+def surrogate_gini_improvements(left_class_counts, left_counts, total_class_counts=None, total_count=None):
+    """strategy.py:32-55: sum_c L_c^2 / n_left + sum_c R_c^2 / n_right for every candidate.  With two
+    arguments the last row holds the totals (cumulative counts down a sorted column)."""
+    if total_class_counts is None:
+        left_class_counts, total_class_counts = left_class_counts[:-1], left_class_counts[-1]
+    if total_count is None:
+        left_counts, total_count = left_counts[:-1], left_counts[-1]
+    right = total_class_counts - left_class_counts
+    return (np.square(left_class_counts).sum(axis=2) / left_counts
+            + np.square(right).sum(axis=2) / (total_count - left_counts))
+
+
+def surrogate_p_at_k_improvements(left_class_counts, left_counts, total_class_counts=None, total_count=None, k=1):
+    """strategy.py:79-100: largest class count left + largest class count right (``k`` is unused there too)."""
+    if total_class_counts is None:
+        left_class_counts, total_class_counts = left_class_counts[:-1], left_class_counts[-1]
+    return np.max(left_class_counts, axis=2) + np.max(total_class_counts - left_class_counts, axis=2)
+
+
+def _gini_from_counts(value, class_counts, n):
+    """surrogate_to_gini (strategy.py:107-108) from the class totals of the node."""
+    return value / n - np.sum(np.square(class_counts / class_counts.sum()))
+
+
+def _p_at_k_from_counts(value, class_counts, n):
+    """surrogate_to_p_at_k (strategy.py:103-104) from the class totals of the node."""
+    return (value - np.max(class_counts)) / n
 
 
 def _labels_of(y):
@@ -68,16 +100,38 @@ def greedy_classification_p_at_k(X, y, k=1):
     return f, thr, surrogate_to_p_at_k(score, np.asarray(y)), np.zeros(F, dtype=bool)
 
 
+def _random_search(X, y, surrogate, to_improvement):
+    from ._rows import RowSession, random_node_search
+    labels, C = _labels_of(y)
+    if np.asarray(X).shape[0] < 1:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    sess = RowSession(X, labels, C)
+    try:
+        best, thr, improvement, _ = random_node_search(sess, 0, 0, sess.N, np.arange(sess.F), sess.root_counts,
+                                                       surrogate, to_improvement)
+        return best, thr, improvement, np.zeros(sess.F, dtype=bool)
+    finally:
+        sess.close()
+
+
+def random_classify(X, y):
+    """strategy.py:149-159: one U(min, max) threshold per column (np.random), best column by gini."""
+    return _random_search(X, y, surrogate_gini_improvements, _gini_from_counts)
+
+
+def random_classify_p_at_k(X, y, k=1):
+    """strategy.py:162-172: the same with the precision-at-1 surrogate."""
+    return _random_search(X, y, surrogate_p_at_k_improvements, _p_at_k_from_counts)
+
+
 def _not_accelerated(name):
     def fn(*args, **kwargs):
         raise NotImplementedError(
-            f"{name} draws random thresholds from np.random per node; only the exhaustive searches "
-            "(greedy_classification, greedy_classification_p_at_k) run on the GPU path")
+            f"{name} (regression with random cuts) is not part of the accelerated path; the classification "
+            "splitters random_classify / random_classify_p_at_k and the exhaustive searches are")
     fn.__name__ = name
     return fn
 
 
-random_classify = _not_accelerated("random_classify")
-random_classify_p_at_k = _not_accelerated("random_classify_p_at_k")
 random_split = _not_accelerated("random_split")
 random_split_v2 = _not_accelerated("random_split_v2")

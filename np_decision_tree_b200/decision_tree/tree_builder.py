@@ -13,6 +13,7 @@ import numpy as np
 from .. import _lib
 from ._common import context_for, matrix_arg
 from .base import DecisionTree
+from . import strategy as _strategy
 from .strategy import (greedy_classification, greedy_classification_p_at_k, random_classify,  # noqa: F401
                        random_classify_p_at_k, random_split, random_split_v2)
 
@@ -27,7 +28,19 @@ def leaf_from_data_classification(y):
     return np.argmax(y.sum(axis=0))
 
 
+def _checked_labels(y, max_classes):
+    """int32 class ids with numpy's index semantics of ``np.eye(max_classes)[y]`` (tree_builder.py:157-158)."""
+    lab = np.asarray(y)
+    if lab.ndim != 1 or not np.issubdtype(lab.dtype, np.integer):
+        raise IndexError("y must be a 1-D array of integer class ids (it indexes np.eye(max_classes))")
+    if lab.size and (lab.min() < -max_classes or lab.max() >= max_classes):
+        raise IndexError(f"index out of bounds for axis 0 with size {max_classes}")
+    return np.ascontiguousarray(np.where(lab < 0, lab + max_classes, lab), dtype=np.int32)
+
+
 _CRITERION = {greedy_classification: _lib.GINI, greedy_classification_p_at_k: _lib.P_AT_1}
+_RANDOM = {random_classify: (_strategy.surrogate_gini_improvements, _strategy._gini_from_counts),
+           random_classify_p_at_k: (_strategy.surrogate_p_at_k_improvements, _strategy._p_at_k_from_counts)}
 
 
 def build_classification_tree(X, y,
@@ -39,13 +52,22 @@ def build_classification_tree(X, y,
                               leaf_from_data=leaf_from_data_classification,
                               max_classes=2):
     """tree_builder.py:149-159 -> build_tree (:56-96).  ``y`` holds integer class ids in
-    ``[0, max_classes)``.  ``split_method`` must be one of this package's exhaustive searches
-    (the reference's default, ``random_classify``, is not accelerated and raises)."""
-    if split_method not in _CRITERION:
-        split_method()     # raises NotImplementedError for the random splitters
-        raise NotImplementedError("split_method must be greedy_classification or greedy_classification_p_at_k")
+    ``[0, max_classes)``.  ``split_method``: this package's ``random_classify`` (the reference's default)
+    / ``random_classify_p_at_k`` -- node-at-a-time, thresholds and column sub-samples drawn from
+    ``np.random`` exactly like the reference -- or the exhaustive ``greedy_classification`` /
+    ``greedy_classification_p_at_k`` (level-synchronous, needs ``max_feature >= X.shape[1]``)."""
+    if split_method not in _CRITERION and split_method not in _RANDOM:
+        raise NotImplementedError("split_method must be one of this module's random_classify, "
+                                  "random_classify_p_at_k, greedy_classification, greedy_classification_p_at_k")
     if leaf_from_data is not leaf_from_data_classification:
         raise NotImplementedError("classification leaves are the most frequent class (leaf_from_data_classification)")
+    if split_method in _RANDOM:
+        from ._rows import grow_random
+        lab = y if (hasattr(y, "data_ptr") and not isinstance(y, np.ndarray)) else _checked_labels(y, max_classes)
+        surrogate, to_improvement = _RANDOM[split_method]
+        return grow_random(DecisionTree(2 ** (max_depth + 1)), X, lab, int(max_classes), int(max_depth),
+                           int(max_feature), float(min_improvement), int(min_sample_leaf), surrogate,
+                           to_improvement).final()
     xp, xs, xk, N, F, ldx = matrix_arg(X)
     if F > max_feature:
         raise NotImplementedError("F > max_feature samples columns with np.random per node "
@@ -55,12 +77,7 @@ def build_classification_tree(X, y,
         lab = y.to(torch.int32).contiguous()
         lp, ls, lk = _lib.as_arg(lab, np.int32, "y")
     else:
-        lab = np.asarray(y)
-        if lab.ndim != 1 or not np.issubdtype(lab.dtype, np.integer):
-            raise IndexError("y must be a 1-D array of integer class ids (it indexes np.eye(max_classes))")
-        if lab.size and (lab.min() < -max_classes or lab.max() >= max_classes):
-            raise IndexError(f"index out of bounds for axis 0 with size {max_classes}")   # np.eye(C)[y]
-        lab = np.ascontiguousarray(np.where(lab < 0, lab + max_classes, lab), dtype=np.int32)
+        lab = _checked_labels(y, max_classes)
         lp, ls, lk = lab.ctypes.data, _lib.HOST, lab
     if xs != ls:
         raise ValueError("X and y must both be host arrays or both be CUDA tensors")

@@ -41,4 +41,6 @@ from .np_tree_oracle import (  # noqa: F401
     p_at_1_surrogate,
     class_split_node,
     fit_classes,
+    random_class_split_node,
+    fit_classes_random,
 )

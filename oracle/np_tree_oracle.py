@@ -559,3 +559,77 @@ def fit_classes(X, labels, n_classes, max_depth=2, max_feature=100, min_improvem
         pending.append((rows[~goes_left], node, False, depth + 1))
         pending.append((rows[goes_left], node, True, depth + 1))
     return tree
+
+
+# --------------------------------------------------------------------------
+# classification with random thresholds (ExtraTree style)   
+# --------------------------------------------------------------------------
+def random_class_split_node(X_node, onehot_node, criterion="gini", rng=np.random):
+    """(column, threshold, improvement) of one node with ONE random threshold per column.
+
+    ref: decision_tree/strategy.py:149-159 (random_classify) and :162-172
+    (random_classify_p_at_k).  The thresholds are ``uniform(column min, column max)``
+    drawn from numpy's GLOBAL generator in column order; rows go left when
+    ``x <= threshold``; the best column is the first argmax of the surrogate
+    (a constant column gives 0/0 = nan, which np.argmax treats as the maximum).
+    """
+    n = X_node.shape[0]
+    thresholds = rng.uniform(X_node.min(axis=0), X_node.max(axis=0))
+    goes_left = X_node <= thresholds
+    left = goes_left.T.astype(np.float64) @ onehot_node          # (F, C) whole numbers
+    n_left = goes_left.sum(axis=0)
+    total = onehot_node.sum(axis=0)
+    right = total - left
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if criterion == "gini":
+            score = np.square(left).sum(axis=1) / n_left + np.square(right).sum(axis=1) / (n - n_left)
+        elif criterion == "p_at_k":
+            score = np.max(left, axis=1) + np.max(right, axis=1)
+        else:
+            raise ValueError(criterion)
+    best = int(np.argmax(score))
+    if criterion == "gini":
+        improvement = score[best] / n - np.sum(np.square(total / onehot_node.sum()))
+    else:
+        improvement = (score[best] - np.max(total)) / n
+    return best, thresholds[best], improvement
+
+
+def fit_classes_random(X, labels, n_classes, max_depth=2, max_feature=100, min_improvement=0.01,
+                       min_sample_leaf=1, criterion="gini", rng=np.random):
+    """Depth-first classification tree with random thresholds and column sub-sampling.
+
+    ref: decision_tree/tree_builder.py:43-52 (find_best_split: all columns when
+    F <= max_feature, else the first max_feature of ``np.random.permutation(columns)``),
+    :56-96 (build_tree), base.py:13-21.  Consumes ``rng`` in the reference's order:
+    per searched node, in depth-first order, [permutation] then F' uniforms.
+    """
+    X = np.asarray(X)
+    labels = np.asarray(labels)
+    onehot = np.eye(n_classes)[labels]
+    all_columns = np.arange(X.shape[1])
+    tree = TreeArrays(max_depth)
+    t = tree.tree_
+    pending = [(np.arange(X.shape[0]), -1, True, 0)]
+    while pending:
+        rows, parent, is_left, depth = pending.pop()
+        tree.max_node_ += 1
+        node = tree.max_node_
+        if parent >= 0:
+            (t.children_left if is_left else t.children_right)[parent] = node
+        Xn, yn = X[rows], onehot[rows]
+        leaf = rows.size <= 2 * min_sample_leaf or np.unique(yn).size <= 1 or depth >= max_depth
+        if not leaf:
+            columns = all_columns if all_columns.size <= max_feature else rng.permutation(all_columns)[:max_feature]
+            best, threshold, improvement = random_class_split_node(Xn[:, columns], yn, criterion, rng)
+            f = columns[best]
+            leaf = improvement < min_improvement
+        if leaf:
+            t.value[node] = np.argmax(yn.sum(axis=0))
+            continue
+        t.feature[node] = f
+        t.threshold[node] = threshold
+        goes_left = Xn[:, f] <= threshold
+        pending.append((rows[~goes_left], node, False, depth + 1))
+        pending.append((rows[goes_left], node, True, depth + 1))
+    return tree

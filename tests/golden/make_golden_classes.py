@@ -57,9 +57,38 @@ def main():
         # the root's single-node search (strategy.py:272-283 / :313-323)
         col, thr, imp, _ = METHODS[crit](X, np.eye(C)[labels])
         out[f"cl_{name}_root"] = np.array([col, thr, imp], dtype=np.float64)
+    # ---- random-threshold splitters (strategy.py:149-172), seeded global generator ---------------------
+    RANDOM = {"gini": strategy.random_classify, "p_at_k": strategy.random_classify_p_at_k}
+    rcases = [("r0", "gini", 90, 300, 6, 3, 5, 6, {}), ("r1", "gini", 91, 1000, 10, 10, 9, 10, dict(min_improvement=1e-7)),
+              ("r2", "gini", 92, 800, 12, 4, 8, 5, dict(min_improvement=1e-7)),          # F > max_feature: permutation
+              ("r3", "p_at_k", 93, 600, 8, 5, 8, 8, dict(min_improvement=1e-7)),
+              ("r4", "p_at_k", 94, 500, 9, 3, 7, 4, dict(min_improvement=0.001, min_sample_leaf=5)),
+              ("r5", "gini", 95, 200, 4, 2, 6, 4, dict(min_improvement=-1.0))]            # + a constant column (nan score)
+    import warnings
+    for name, crit, seed, n, F, C, depth, max_feature, kw in rcases:
+        X, labels = class_problem(seed, n, F, C)
+        if name == "r5":
+            X[:, 2] = 1.5
+        np.random.seed(1000 + seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = tree_builder.build_classification_tree(X, labels, max_depth=depth, max_feature=max_feature,
+                                                       split_method=RANDOM[crit], max_classes=C, **kw)
+        out.update({f"rc_{name}_X": X, f"rc_{name}_labels": labels, f"rc_{name}_depth": np.int64(depth),
+                    f"rc_{name}_classes": np.int64(C), f"rc_{name}_criterion": np.array(crit),
+                    f"rc_{name}_max_feature": np.int64(max_feature), f"rc_{name}_seed": np.int64(1000 + seed),
+                    f"rc_{name}_min_improvement": np.float64(kw.get("min_improvement", 0.01)),
+                    f"rc_{name}_min_sample_leaf": np.int64(kw.get("min_sample_leaf", 1))})
+        out.update(tree_dict(f"rc_{name}_", t))
+        out[f"rc_{name}_pred"] = utils.inference(X, t)
+        np.random.seed(77)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            col, thr, imp, _ = RANDOM[crit](X, np.eye(C)[labels])
+        out[f"rc_{name}_root"] = np.array([col, thr, imp], dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "reference_classes.npz"), **out)
     print("reference_classes.npz", os.path.getsize(os.path.join(HERE, "reference_classes.npz")), "bytes",
-          {k[3:-9]: int(out[k]) + 1 for k in out if k.endswith("_max_node")})
+          {k[:-9]: int(out[k]) + 1 for k in out if k.endswith("_max_node")})
 
 
 if __name__ == "__main__":

@@ -141,8 +141,10 @@ def test_classification_mirror_rejects_what_is_not_accelerated():
     from np_decision_tree_b200.decision_tree import strategy, tree_builder
     X = np.random.RandomState(0).standard_normal((20, 5))
     y = np.arange(20) % 2
-    with pytest.raises(NotImplementedError, match="random"):
-        tree_builder.build_classification_tree(X, y)                       # reference default: random_classify
+    with pytest.raises(NotImplementedError, match="split_method"):
+        tree_builder.build_classification_tree(X, y, split_method=strategy.random_split)   # regression splitter
+    with pytest.raises(NotImplementedError, match="random cuts"):
+        strategy.random_split_v2(X, y)
     with pytest.raises(NotImplementedError, match="max_feature"):
         tree_builder.build_classification_tree(X, y, max_feature=3, split_method=strategy.greedy_classification)
     with pytest.raises(IndexError):
@@ -150,3 +152,8 @@ def test_classification_mirror_rejects_what_is_not_accelerated():
     with pytest.raises(ValueError, match="one-hot"):
         strategy.greedy_classification(X, np.ones((20, 2)))
     assert strategy.surrogate_to_gini(30.0, np.eye(2)[y]) == 30.0 / 20 - 0.5
+    # host helpers with the reference's two calling conventions (strategy.py:32-55)
+    cum = np.cumsum(np.eye(2)[y][:, np.newaxis, :], axis=0)               # (n, 1, C) running class counts
+    a = strategy.surrogate_gini_improvements(cum, np.arange(1, 21)[:, np.newaxis])
+    b = strategy.surrogate_gini_improvements(cum[:-1], np.arange(1, 20)[:, np.newaxis], cum[-1], 20)
+    assert a.shape == (19, 1) and np.array_equal(a, b)

@@ -135,3 +135,76 @@ def test_errors(mods):
     with pytest.raises(B200Error, match="single row"):
         tree_builder.build_classification_tree(X, labels, max_depth=12, min_sample_leaf=0, min_improvement=-1.0,
                                                split_method=strategy.greedy_classification, max_classes=3)
+
+
+# ---- random-threshold splitters (csrc/rows.cu): seeded np.random must reproduce the reference ----------
+RANDOM_CASES = ["r0", "r1", "r2", "r3", "r4", "r5"]
+
+
+def random_method_of(strategy, criterion):
+    return strategy.random_classify if criterion == "gini" else strategy.random_classify_p_at_k
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_random_tree_matches_reference_golden(golden_classes, mods, name):
+    strategy, tree_builder, utils = mods
+    g, p = golden_classes, f"rc_{name}_"
+    np.random.seed(int(g[p + "seed"]))
+    t = tree_builder.build_classification_tree(
+        g[p + "X"], g[p + "labels"], max_depth=int(g[p + "depth"]), max_feature=int(g[p + "max_feature"]),
+        min_improvement=float(g[p + "min_improvement"]), min_sample_leaf=int(g[p + "min_sample_leaf"]),
+        split_method=random_method_of(strategy, str(g[p + "criterion"])), max_classes=int(g[p + "classes"]))
+    assert_same_tree(t, GoldenTree(g, p), leaf_rtol=0.0, what=name)
+    assert np.array_equal(utils.inference(g[p + "X"], t), g[p + "pred"])
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_random_root_search_matches_reference_golden(golden_classes, mods, name):
+    strategy, _, _ = mods
+    g, p = golden_classes, f"rc_{name}_"
+    C = int(g[p + "classes"])
+    np.random.seed(77)
+    col, thr, imp, const = random_method_of(strategy, str(g[p + "criterion"]))(g[p + "X"], np.eye(C)[g[p + "labels"]])
+    want = g[p + "root"]
+    assert (col, thr) == (int(want[0]), want[1])
+    assert imp == want[2] or (np.isnan(imp) and np.isnan(want[2]))
+    assert const.dtype == bool and not const.any()
+
+
+@pytest.mark.parametrize("criterion", ["gini", "p_at_k"])
+@pytest.mark.parametrize("seed,n,F,C,depth,max_feature", [(51, 20000, 24, 6, 10, 24), (52, 5000, 300, 3, 7, 40),
+                                                           (53, 3000, 5, 40, 9, 5)])
+def test_random_tree_matches_oracle(mods, criterion, seed, n, F, C, depth, max_feature):
+    strategy, tree_builder, utils = mods
+    X, labels = class_problem(seed, n, F, C)
+    kw = dict(max_depth=depth, max_feature=max_feature, min_improvement=1e-7, min_sample_leaf=1)
+    np.random.seed(seed)
+    want = oracle.fit_classes_random(X, labels, C, criterion=criterion, **kw)
+    np.random.seed(seed)
+    got = tree_builder.build_classification_tree(X, labels, split_method=random_method_of(strategy, criterion),
+                                                 max_classes=C, **kw)
+    assert_same_tree(got, want, leaf_rtol=0.0, what=f"random {criterion} seed {seed}")
+    assert np.array_equal(utils.inference(X, got), oracle.predict(X, want))
+
+
+def test_reference_default_split_method_runs(mods):
+    """tree_builder.build_classification_tree's default splitter is random_classify (tree_builder.py:153)."""
+    _, tree_builder, _ = mods
+    X, labels = class_problem(54, 2000, 8, 2)
+    np.random.seed(5)
+    want = oracle.fit_classes_random(X, labels, 2)
+    np.random.seed(5)
+    got = tree_builder.build_classification_tree(X, labels)
+    assert_same_tree(got, want, leaf_rtol=0.0)
+
+
+def test_random_tree_torch_cuda_inputs(mods):
+    import torch
+    strategy, tree_builder, _ = mods
+    X, labels = class_problem(55, 4000, 10, 4)
+    kw = dict(max_depth=6, max_feature=6, min_improvement=1e-7, split_method=strategy.random_classify, max_classes=4)
+    np.random.seed(9)
+    host = tree_builder.build_classification_tree(X, labels, **kw)
+    np.random.seed(9)
+    dev = tree_builder.build_classification_tree(torch.from_numpy(X).cuda(), torch.from_numpy(labels).cuda(), **kw)
+    assert_same_tree(dev, host, leaf_rtol=0.0)

@@ -50,3 +50,34 @@ def test_equal_feature_values_never_straddle_a_split():
         rows = X[leaf == node]
         assert rows.shape[0] > 0
     assert t.node_count >= 3
+
+
+# ---- random-threshold splitters: the oracle must consume numpy's global generator like the reference ----
+RANDOM_CASES = ["r0", "r1", "r2", "r3", "r4", "r5"]
+
+
+def random_case_args(g, name):
+    p = f"rc_{name}_"
+    return dict(X=g[p + "X"], labels=g[p + "labels"], n_classes=int(g[p + "classes"]),
+                max_depth=int(g[p + "depth"]), max_feature=int(g[p + "max_feature"]),
+                min_improvement=float(g[p + "min_improvement"]),
+                min_sample_leaf=int(g[p + "min_sample_leaf"]), criterion=str(g[p + "criterion"]))
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_oracle_random_tree_matches_reference(golden_classes, name):
+    a = random_case_args(golden_classes, name)
+    np.random.seed(int(golden_classes[f"rc_{name}_seed"]))
+    t = oracle.fit_classes_random(**a)
+    assert_same_tree(t, GoldenTree(golden_classes, f"rc_{name}_"), leaf_rtol=0.0, what=name)
+    assert np.array_equal(oracle.predict(a["X"], t), golden_classes[f"rc_{name}_pred"])
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_oracle_random_root_search_matches_reference(golden_classes, name):
+    a = random_case_args(golden_classes, name)
+    np.random.seed(77)
+    f, thr, imp = oracle.random_class_split_node(a["X"], np.eye(a["n_classes"])[a["labels"]], a["criterion"])
+    want = golden_classes[f"rc_{name}_root"]
+    assert f == int(want[0]) and thr == want[1]
+    assert imp == want[2] or (np.isnan(imp) and np.isnan(want[2]))
