@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) rows_columns_kernel(const double *__restr
                                                            const int *__restrict__ labels, int C,
                                                            const double *__restrict__ thr,
                                                            unsigned long long *counts) {                // COUNTS
-    extern __shared__ int sh[];   // COUNTS: [n_cols][C]
+    extern __shared__ int sh[];   // COUNTS: [C][n_cols]
     const int tx = threadIdx.x % cw, ty = threadIdx.x / cw, rpb = 256 / cw;
     if (COUNTS) {
         for (int i = threadIdx.x; i < n_cols * C; i += 256) sh[i] = 0;
@@ -97,15 +97,28 @@ __global__ void __launch_bounds__(256) rows_columns_kernel(const double *__restr
         const int col = has_col ? cols[ci] : 0;
         const double t = (COUNTS && has_col) ? thr[ci] : 0.0;
         double lo = CUDART_INF, hi = -CUDART_INF;
-        for (int64_t r = (int64_t)blockIdx.x * rpb + ty; r < n; r += (int64_t)gridDim.x * rpb) {
-            if (!has_col) continue;
-            const int row = rows[r];
-            const double x = X[(int64_t)row * ldx + col];
+        const int64_t step = (int64_t)gridDim.x * rpb;
+        // four rows in flight per thread: the loads of a row do not depend on the previous row
+        for (int64_t r = (int64_t)blockIdx.x * rpb + ty; r < n; r += 4 * step) {
+            int row[4];
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) row[u] = (r + u * step < n) ? rows[r + u * step] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = (row[u] >= 0 && has_col) ? X[(int64_t)row[u] * ldx + col] : CUDART_NAN;
             if (COUNTS) {
-                if (x <= t) atomicAdd(&sh[ci * C + labels[row]], 1);   // strategy.py:151-152: masks = X <= thresholds
+                int lab[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) lab[u] = (row[u] >= 0 && has_col) ? labels[row[u]] : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)   // strategy.py:151-152: masks = X <= thresholds (NaN compares false)
+                    if (x[u] <= t) atomicAdd(&sh[lab[u] * n_cols + ci], 1);
             } else {
-                lo = fmin(lo, x);
-                hi = fmax(hi, x);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    lo = fmin(lo, x[u]);   // fmin / fmax ignore the NaN of an absent row
+                    hi = fmax(hi, x[u]);
+                }
             }
         }
         if (!COUNTS && has_col && lo <= hi) {
@@ -115,8 +128,9 @@ __global__ void __launch_bounds__(256) rows_columns_kernel(const double *__restr
     }
     if (COUNTS) {
         __syncthreads();
+        // shared layout is [class][column] (consecutive threads = consecutive columns: no bank conflicts)
         for (int i = threadIdx.x; i < n_cols * C; i += 256)
-            if (sh[i]) atomicAdd(counts + i, (unsigned long long)sh[i]);
+            if (sh[i]) atomicAdd(counts + (size_t)(i % n_cols) * C + i / n_cols, (unsigned long long)sh[i]);
     }
 }
 

@@ -117,7 +117,9 @@ if "cls" in args:
     N = int(os.environ.get("CLS_ROWS", 10_000_000))
     F = int(os.environ.get("CLS_FEATURES", 256))
     C = int(os.environ.get("CLS_CLASSES", 8))
-    crit = strategy.greedy_classification_p_at_k if os.environ.get("CLS_CRIT") == "p_at_k" else strategy.greedy_classification
+    crit = {"p_at_k": strategy.greedy_classification_p_at_k, "random": strategy.random_classify,
+            "random_p_at_k": strategy.random_classify_p_at_k}.get(os.environ.get("CLS_CRIT"), strategy.greedy_classification)
+    is_random = crit in (strategy.random_classify, strategy.random_classify_p_at_k)
     g = torch.Generator(device="cuda")
     g.manual_seed(0)
     X = torch.empty((N, F), dtype=torch.float64, device="cuda")
@@ -131,6 +133,7 @@ if "cls" in args:
     ctx = _lib.default_context(0)
     ctx.profile_enable(True)
     ctx.profile_reset()
+    np.random.seed(0)
     t_fit, tree = best_of(lambda: tree_builder.build_classification_tree(X, labels, **kw), n=3)
     prof = ctx.profile()
     ctx.profile_enable(False)
@@ -147,9 +150,14 @@ if "cls" in args:
         Xc = X[:n_s, :f_s].cpu().numpy()
         lc = labels[:n_s].cpu().numpy().astype(np.int64)
         t0 = time.perf_counter()
-        o = oracle.fit_classes(Xc, lc, C, max_depth=10, max_feature=f_s, min_improvement=1e-7,
-                               criterion="p_at_k" if crit is strategy.greedy_classification_p_at_k else "gini")
+        cname = "p_at_k" if "p_at_k" in crit.__name__ else "gini"
+        np.random.seed(0)
+        if is_random:
+            o = oracle.fit_classes_random(Xc, lc, C, max_depth=10, max_feature=f_s, min_improvement=1e-7, criterion=cname)
+        else:
+            o = oracle.fit_classes(Xc, lc, C, max_depth=10, max_feature=f_s, min_improvement=1e-7, criterion=cname)
         dt = time.perf_counter() - t0
+        np.random.seed(0)
         g = tree_builder.build_classification_tree(Xc, lc, max_depth=10, max_feature=f_s, min_improvement=1e-7,
                                                    split_method=crit, max_classes=C)
         same = all(np.array_equal(getattr(g.tree_, k), getattr(o.tree_, k))

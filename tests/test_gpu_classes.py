@@ -208,3 +208,20 @@ def test_random_tree_torch_cuda_inputs(mods):
     np.random.seed(9)
     dev = tree_builder.build_classification_tree(torch.from_numpy(X).cuda(), torch.from_numpy(labels).cuda(), **kw)
     assert_same_tree(dev, host, leaf_rtol=0.0)
+
+
+def test_estimator_wrapper_cross_val():
+    """run_classification.py:18-38,43-52: the Mree estimator under sklearn's cross_val_score."""
+    from sklearn.model_selection import cross_val_score
+    from np_decision_tree_b200.estimator import Mree
+    from np_decision_tree_b200.decision_tree import strategy
+    X, labels = class_problem(61, 3000, 6, 3, noise=0.2)
+
+    def scorer(est, x, y):
+        return float(np.mean(est.predict(x) == y))
+
+    for method, mf in ((strategy.greedy_classification, 6), (strategy.random_classify, 4)):
+        np.random.seed(3)
+        scores = cross_val_score(Mree(max_depth=8, max_feature=mf, max_classes=3, split_method=method), X, labels,
+                                 cv=3, scoring=scorer)
+        assert scores.shape == (3,) and scores.min() > 0.5, (method.__name__, scores)
