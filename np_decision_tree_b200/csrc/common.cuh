@@ -79,6 +79,7 @@ struct b200dt_ctx {
     // epoch of the look-back flag words: monotonic per context because the status buffers are
     // reused across sessions (a stale flag of an old launch must never look current)
     u32 epoch = 0;
+    u32 attr_mask = 0;  // which kernels already had their dynamic shared-memory limit raised on this device
 
     // named grow-only scratch buffers (no allocation in steady state)
     std::vector<DevBuf> scratch;

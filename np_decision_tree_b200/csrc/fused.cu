@@ -220,11 +220,11 @@ int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, i
     const int64_t total = (int64_t)n_tiles * F_store;
     const void *kern = variant == 1 ? (const void *)level_fused_kernel<1> : (const void *)level_fused_kernel<2>;
     const size_t smem = 16 * SY_PITCH * sizeof(double) + 8 * 16 * sizeof(u32);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // (per context = per device: a process may drive several GPUs)
+    if (!(ctx->attr_mask & 1u)) {
         CK(cudaFuncSetAttribute(level_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(level_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ctx->attr_mask |= 1u;
     }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;

@@ -635,10 +635,10 @@ int launch_walk(b200dt_ctx *ctx, const int *orders, int64_t stride, int F, const
         CKR(scratch_get(ctx, SB_L1_H, (size_t)n_walks * words * 4, (void **)&gbm));
         use_smem = 16;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    // (per context = per device: a process may drive several GPUs)
+    if (!(ctx->attr_mask & 2u)) {
         CK(cudaFuncSetAttribute(l1_median_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK_SMEM_MAX));
-        attr_done = true;
+        ctx->attr_mask |= 2u;
     }
     LaunchScope ls(ctx, KC_L1_DESCENT, 16.0 * (double)n_elems * F * 2);
     l1_median_walk_kernel<<<(unsigned)((int64_t)n_walks * P), 32, use_smem, ctx->stream>>>(

@@ -475,11 +475,11 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
     if (a.ypay) {
         // streaming kernel: tiles of ST_TILE positions (the host builds the tile list accordingly)
         const size_t smem = 8 * ST_PITCH * sizeof(double);
-        static bool attr_done = false;
-        if (!attr_done) {
+        // (per context = per device: a process may drive several GPUs)
+        if (!(ctx->attr_mask & 4u)) {
             CK(cudaFuncSetAttribute(l2_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(l2_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
+            ctx->attr_mask |= 4u;
         }
         const void *kern = variant == 1 ? (const void *)l2_scan_stream_kernel<1> : (const void *)l2_scan_stream_kernel<2>;
         int per_sm = 0;

@@ -77,10 +77,10 @@ int predict_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int6
     const double bytes = (32.0 * avg_path_hint + (d_out_value ? 8.0 : 0.0) + (d_out_leaf ? 4.0 : 0.0)) * (double)N;
     LaunchScope ls(ctx, KC_PREDICT, bytes);
     if (smem <= 200 * 1024) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        // (per context = per device: a process may drive several GPUs)
+        if (!(ctx->attr_mask & 8u)) {
             CK(cudaFuncSetAttribute(predict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
+            ctx->attr_mask |= 8u;
         }
         predict_kernel<true><<<(unsigned)blocks, 256, smem, ctx->stream>>>(dX, N, F, ldx, t, n_nodes, d_out_value, d_out_leaf);
     } else {

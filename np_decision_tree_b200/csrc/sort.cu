@@ -453,13 +453,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
     const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
     const size_t prep_smem = PREP_COLS * NPASS * 256 * 4 + PREP_COLS * PREP_PITCH * sizeof(KeyT);
     const size_t pass_smem = sizeof(RsSmem<KeyT>);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // (per context = per device: a process may drive several GPUs)
+    if (!(ctx->attr_mask & 16u)) {
         CK(cudaFuncSetAttribute(sort_prepare_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-        attr_done = true;
+        ctx->attr_mask |= 16u;
     }
     CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
     {

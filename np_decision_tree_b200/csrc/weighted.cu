@@ -210,10 +210,10 @@ int launch_l2w_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, 
     if (n_tiles <= 0) return 0;
     const int64_t total = (int64_t)n_tiles * a.F_search;
     const size_t smem = 16 * SY_PITCH * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // (per context = per device: a process may drive several GPUs)
+    if (!(ctx->attr_mask & 32u)) {
         CK(cudaFuncSetAttribute(l2w_scan_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ctx->attr_mask |= 32u;
     }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2w_scan_stream_kernel, 256, smem) != cudaSuccess ||
