@@ -454,12 +454,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
     const size_t prep_smem = PREP_COLS * NPASS * 256 * 4 + PREP_COLS * PREP_PITCH * sizeof(KeyT);
     const size_t pass_smem = sizeof(RsSmem<KeyT>);
     // (per context = per device: a process may drive several GPUs)
-    if (!(ctx->attr_mask & 16u)) {
+    const u32 attr_bit = sizeof(KeyT) == 4 ? 16u : 64u;   // this function is instantiated per key type
+    if (!(ctx->attr_mask & attr_bit)) {
         CK(cudaFuncSetAttribute(sort_prepare_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
         CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-        ctx->attr_mask |= 16u;
+        ctx->attr_mask |= attr_bit;
     }
     CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
     {
