@@ -36,6 +36,7 @@ enum KernelClass {
     KC_CLASS_HIST,        // classification: per-tile class histograms
     KC_CLASS_SCORE,       // classification: gini / precision-at-1 scores + argmax
     KC_ROWS,              // random-threshold splitters: column min/max, threshold counts, row-list split
+    KC_CHILD_SCAN,        // two-level search: both children scored from the parent's order (side-bit look-up)
     KC_COUNT
 };
 
@@ -43,7 +44,7 @@ static const char *const kKernelClassNames[KC_COUNT] = {
     "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
     "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
     "misc", "level_fused_partition_search", "gather_y_payload", "sort_fixup_ties", "class_tile_histogram",
-    "class_score_search", "row_list_ops"};
+    "class_score_search", "row_list_ops", "l2_children_scan_search"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -119,7 +120,7 @@ enum ScratchId {
     SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
     SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
     SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
-    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_COUNT
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_MASK_A, SB_CODES, SB_PLAN4, SB_COUNT
 };
 
 static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {
@@ -312,6 +313,8 @@ struct Partial {
     double score2;  // best score among the other candidates seen
     int k;          // position inside the node, -1 = none
     int f;          // local column
+    int ppos;       // two-level search: position of that row inside the PARENT's segment (data not yet moved); else -1
+    int pad_;
 };
 
 // cross-file entry points (host side)

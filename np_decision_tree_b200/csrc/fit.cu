@@ -234,6 +234,8 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     {
         const char *e = getenv("B200DT_FUSE");
         s->fuse_levels = e && e[0] == '1';
+        const char *t = getenv("B200DT_TWO_LEVEL");
+        s->two_level = t && t[0] == '1';
     }
     if (criterion == B200DT_L2) {
         // y-payload double buffer; idle during the sort, so it doubles as the radix key scratch
@@ -336,6 +338,8 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
         sg.exact = (nd.n <= EXACT_MAX_ROWS || s->force_exact[i]) ? 1 : 0;
         sg.pstep = 1;
         sg.pside = 0;
+        sg.vstart = -1;
+        sg.vpad = 0;
         sg.pbase = pbase;
         sg.np = sg.exact ? 1 : ntiles;
         const bool from_parent = nd.has_fused && !sg.exact;
@@ -344,6 +348,7 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
             sg.np = nd.fp_np;
             sg.pstep = 2;
             sg.pside = nd.fp_side;
+            sg.vstart = nd.vstart;   // >= 0: searched from its parent's order, rows not moved yet (children.cu)
         }
         pbase += nd.has_fused ? 1 : ntiles;
         s->h_segs[i] = sg;
@@ -365,6 +370,8 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     return 0;
 }
 
+static int materialise_pending(b200dt_ctx *ctx);
+
 static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool exact_only) {
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
@@ -375,6 +382,12 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
             return ctx->fail_msg("fit: attempt to split a node with a single row (min_sample_leaf < 1); "
                                  "the reference raises ValueError here (argmax of an empty sequence)");
     if (s->criterion == B200DT_L1) return l1_level_search(ctx, s, d_out, exact_only);
+    if (s->pending && exact_only) {
+        // near tie on the second level of a pair: move the rows (plain partition), then search this level again
+        // in the ordinary way (sequential order for the flagged nodes, parallel scan for the others)
+        CKR(materialise_pending(ctx));
+        exact_only = false;
+    }
     std::vector<TileDesc> tiles;
     std::vector<int> small;
     int64_t tile_elems, small_elems;
@@ -485,7 +498,18 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     s->plan_tiles.clear();
     s->plan_elems = 0;
     s->next_fused_slots = 0;
+    s->plan_parents.clear();
+    s->plan_two_level = false;
     const bool payload = s->ypay[0] != nullptr && s->fuse_levels && !s->dw;
+    // two levels per data movement (children.cu): this level's children may be searched from the parents' order
+    // (first level of a pair), or the live nodes already are such children (second level: `was_pending`)
+    const bool was_pending = s->pending;
+    const bool pair_candidate = s->two_level && !was_pending && !payload && s->ypay[0] != nullptr && !s->dw &&
+                                s->criterion == B200DT_L2;
+    std::vector<PlanSeg> pair_plan;        // one per plan seg, filled while the plan is built
+    std::vector<int> pair_children;        // (left child, right child) node ids per plan seg
+    std::vector<int> vmarks;               // [f, parent start, parent position, side] of virtual split nodes
+    int max_vspan = 0;
     for (int i = 0; i < n_live; ++i) {
         const int nid = s->live[i];
         const b200dt_candidate &w = win[i];
@@ -544,10 +568,26 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             sg.exact = 0;
             sg.pstep = 1;
             sg.pside = 0;
+            sg.vstart = -1;
+            sg.vpad = 0;
             const int si = (int)s->plan_segs.size();
             s->plan_segs.push_back(sg);
             for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{si, t});
             s->plan_elems += n;
+            s->plan_parents.push_back(PendParent{nid, start, n, nl});
+            if (pair_candidate) {
+                PlanSeg ps;
+                ps.total_l = w.left_sum;
+                ps.total_r = total - w.left_sum;
+                ps.start = start;
+                ps.n = n;
+                ps.nleft = nl;
+                ps.fbase = 0;
+                ps.score_l = ps.score_r = 0;
+                pair_plan.push_back(ps);
+                pair_children.push_back(lc);
+                pair_children.push_back(rc);
+            }
             if (payload) {
                 // the fused level kernel scores the children that the next level searches by scan
                 PlanSeg ps;
@@ -573,21 +613,66 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             }
             const int fl = w.f - s->col_offset;
             if (fl >= 0 && fl < s->F_local) {  // this rank owns the winning column: it marks the left rows
-                marks.push_back(fl);
-                marks.push_back(start);
-                marks.push_back(w.k);
-                max_left = std::max(max_left, nl);
+                const HNode &me = s->nodes[nid];
+                if (me.vstart >= 0) {
+                    // the node's rows have not been moved: its left rows are the rows of its side up to the
+                    // winner's position in the PARENT's order (candidate.pad)
+                    vmarks.push_back(fl);
+                    vmarks.push_back(me.vstart);
+                    vmarks.push_back(w.pad);
+                    vmarks.push_back(me.fp_side);
+                    max_vspan = std::max(max_vspan, w.pad + 1);
+                } else {
+                    marks.push_back(fl);
+                    marks.push_back(start);
+                    marks.push_back(w.k);
+                    max_left = std::max(max_left, nl);
+                }
             }
         }
     }
     if (!s->plan_segs.empty()) {
         *need_partition = 1;
         CK(cudaMemsetAsync(d_mask, 0, (size_t)((s->N + 31) / 32) * 4, ctx->stream));
+        int *d_marks;
+        CKR(scratch_get(ctx, SB_TMP_I64, (marks.size() + vmarks.size()) * 4 + 128, (void **)&d_marks));
         if (!marks.empty()) {
-            int *d_marks;
-            CKR(scratch_get(ctx, SB_TMP_I64, marks.size() * 4 + 64, (void **)&d_marks));
             CKR(upload(ctx, PIN_PLAN, 0, marks.data(), marks.size(), d_marks));
             CKR(launch_mark_left(ctx, s->ord[s->cur], s->col_stride, d_marks, (int)marks.size() / 3, max_left, d_mask));
+        }
+        if (!vmarks.empty()) {
+            int *d_vmarks = d_marks + (marks.size() + 15) / 16 * 16;
+            CKR(upload(ctx, PIN_PLAN, (marks.size() + 15) / 16 * 64, vmarks.data(), vmarks.size(), d_vmarks));
+            CKR(launch_mark_left_virtual(ctx, s->ord[s->cur], s->col_stride, d_vmarks, (int)vmarks.size() / 4, max_vspan,
+                                         s->d_mask_a, d_mask));
+        }
+    }
+    // first level of a pair?  Only if every node the next level searches is large enough for the parallel scan
+    // (the sequential exact kernel needs the node's rows in place)
+    if (pair_candidate && !s->plan_segs.empty() && !next_live.empty()) {
+        bool ok = true;
+        for (int c : next_live) ok = ok && s->nodes[c].n > EXACT_MAX_ROWS;
+        if (ok) {
+            int slots = 0;
+            for (size_t i = 0; i < pair_plan.size(); ++i) {
+                PlanSeg &ps = pair_plan[i];
+                const int np = (ps.n + ST_TILE - 1) / ST_TILE;
+                ps.fbase = slots;
+                for (int side = 0; side < 2; ++side) {
+                    HNode &ch = s->nodes[pair_children[2 * i + side]];
+                    if (ch.leaf) continue;
+                    ch.has_fused = true;
+                    ch.fp_base = ps.fbase;
+                    ch.fp_np = np;
+                    ch.fp_side = side;
+                    ch.vstart = ps.start;
+                    (side == 0 ? ps.score_l : ps.score_r) = 1;
+                }
+                slots += 2 * np;
+            }
+            s->next_fused_slots = slots;
+            s->plan_fused = pair_plan;
+            s->plan_two_level = true;
         }
     }
     // candidate slots the next level needs: the fused ones + each live node's own reserve (this must
@@ -605,10 +690,133 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     return 0;
 }
 
+// The rows of the pending level's nodes still lie in their parents' segments: move them now with the plain
+// binary partition (mask of the first level of the pair).  Used when the second level needs its rows in place.
+static int materialise_pending(b200dt_ctx *ctx) {
+    Session *s = ctx->session;
+    if (!s->pending) return 0;
+    SegDev *d_segs;
+    TileDesc *d_tiles;
+    u64 *pstatus;
+    const size_t seg_bytes = s->pend_segs.size() * sizeof(SegDev);
+    CKR(scratch_get(ctx, SB_SEG, seg_bytes + 64, (void **)&d_segs));
+    CKR(scratch_get(ctx, SB_TILES, s->pend_tiles.size() * sizeof(TileDesc) + 64, (void **)&d_tiles));
+    CKR(upload(ctx, PIN_PLAN, 0, s->pend_segs.data(), s->pend_segs.size(), d_segs));
+    CKR(upload(ctx, PIN_PLAN, seg_bytes + 64, s->pend_tiles.data(), s->pend_tiles.size(), d_tiles));
+    CKR(scratch_get(ctx, SB_STATUS_P, (s->pend_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
+    CKR(next_epoch(ctx));
+    CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
+                         (int)s->pend_tiles.size(), s->pend_elems, s->d_mask_a, pstatus, ctx->epoch, nullptr,
+                         s->ypay[s->cur], s->ypay[s->cur ^ 1], nullptr, nullptr));
+    s->cur ^= 1;
+    for (int c : s->live) {
+        s->nodes[c].has_fused = false;
+        s->nodes[c].vstart = -1;
+    }
+    s->fused_slots = 0;
+    s->pending = false;
+    s->pend.clear();
+    s->pend_segs.clear();
+    s->pend_tiles.clear();
+    return 0;
+}
+
 static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     if (s->plan_segs.empty()) return 0;
+    const size_t mask_bytes = (size_t)((s->N + 31) / 32) * 4;
+    if (s->pending) {
+        // second level of a pair: ONE 4-way partition moves the rows for both levels (children.cu)
+        std::vector<Plan4> plan4;
+        std::vector<TileDesc> tiles4;
+        int64_t elems = 0;
+        std::vector<char> is_live(s->nodes.size(), 0);
+        for (int c : s->live) is_live[c] = 1;
+        for (const PendParent &pp : s->pend) {
+            const HNode &par = s->nodes[pp.node];
+            Plan4 p4;
+            p4.start = pp.start;
+            p4.n = pp.n;
+            p4.n_l = pp.nleft;
+            p4.n_ll = p4.n_rl = 0;
+            p4.pad = 0;
+            bool needed = false;
+            for (int side = 0; side < 2; ++side) {
+                const HNode &ch = s->nodes[side == 0 ? par.left : par.right];
+                // a child that is a leaf, or whose split has no grandchild to search (decide marks no rows for
+                // it): all its rows keep code B = 0 and stay together, in order
+                if (ch.left < 0 || !(is_live[ch.left] || is_live[ch.right])) continue;
+                (side == 0 ? p4.n_ll : p4.n_rl) = s->nodes[ch.left].n;
+                needed = true;
+            }
+            if (!needed) continue;
+            const int si = (int)plan4.size();
+            plan4.push_back(p4);
+            for (int t = 0; t < (pp.n + PT_TILE - 1) / PT_TILE; ++t) tiles4.push_back(TileDesc{si, t});
+            elems += pp.n;
+        }
+        if (!plan4.empty()) {
+            Plan4 *d_plan4;
+            TileDesc *d_tiles;
+            u32 *d_codes;
+            u64 *pstatus;
+            CKR(scratch_get(ctx, SB_PLAN4, plan4.size() * sizeof(Plan4) + 64, (void **)&d_plan4));
+            CKR(scratch_get(ctx, SB_TILES, tiles4.size() * sizeof(TileDesc) + 64, (void **)&d_tiles));
+            CKR(scratch_get(ctx, SB_CODES, 2 * mask_bytes + 64, (void **)&d_codes));
+            const size_t mark_bytes = (size_t)s->plan_segs.size() * 32 + 256;   // marks staged first in PIN_PLAN
+            CKR(upload(ctx, PIN_PLAN, mark_bytes, plan4.data(), plan4.size(), d_plan4));
+            CKR(upload(ctx, PIN_PLAN, mark_bytes + plan4.size() * sizeof(Plan4) + 64, tiles4.data(), tiles4.size(), d_tiles));
+            CKR(scratch_get(ctx, SB_STATUS_P, (tiles4.size() * (size_t)s->F_store + 1) * 48, (void **)&pstatus, true));
+            CKR(next_epoch(ctx));
+            CKR(launch_partition4(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->ypay[s->cur], s->ypay[s->cur ^ 1],
+                                  s->col_stride, s->F_store, d_plan4, d_tiles, (int)tiles4.size(), elems, s->d_mask_a,
+                                  d_mask, s->N, d_codes, pstatus, ctx->epoch));
+            s->cur ^= 1;
+        }
+        s->pending = false;
+        s->pend.clear();
+        s->pend_segs.clear();
+        s->pend_tiles.clear();
+        s->plan_segs.clear();
+        s->plan_fused.clear();
+        s->plan_tiles.clear();
+        return 0;
+    }
+    if (s->plan_two_level) {
+        // first level of a pair: nothing moves; the children are searched from the parents' order
+        CKR(scratch_get(ctx, SB_MASK_A, mask_bytes + 64, (void **)&s->d_mask_a));
+        CK(cudaMemcpyAsync(s->d_mask_a, d_mask, mask_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        std::vector<TileDesc> stiles;
+        for (size_t i = 0; i < s->plan_fused.size(); ++i)
+            for (int t = 0; t < (s->plan_fused[i].n + ST_TILE - 1) / ST_TILE; ++t) stiles.push_back(TileDesc{(int)i, t});
+        PlanSeg *d_plan;
+        TileDesc *d_tiles;
+        u64 *pstatus;
+        const size_t plan_bytes = s->plan_fused.size() * sizeof(PlanSeg);
+        const size_t mark_bytes = (size_t)s->plan_segs.size() * 32 + 256;
+        CKR(scratch_get(ctx, SB_PLAN, plan_bytes + 64, (void **)&d_plan));
+        CKR(scratch_get(ctx, SB_TILES, stiles.size() * sizeof(TileDesc) + 64, (void **)&d_tiles));
+        CKR(upload(ctx, PIN_PLAN, mark_bytes, s->plan_fused.data(), s->plan_fused.size(), d_plan));
+        CKR(upload(ctx, PIN_PLAN, mark_bytes + plan_bytes + 64, stiles.data(), stiles.size(), d_tiles));
+        CKR(scratch_get(ctx, SB_STATUS_P, (stiles.size() * (size_t)s->F_local + 1) * 48, (void **)&pstatus, true));
+        CKR(scratch_get(ctx, SB_PARTIAL, (s->next_partial_slots + 1) * s->F_local * sizeof(Partial) + 64,
+                        (void **)&s->d_partials));
+        CKR(next_epoch(ctx));
+        CKR(launch_children_scan(ctx, s->ord[s->cur], s->ypay[s->cur], s->col_stride, s->F_local, d_plan, d_tiles,
+                                 (int)stiles.size(), s->plan_elems, s->d_mask_a, pstatus, ctx->epoch, s->d_partials,
+                                 s->variant));
+        s->pending = true;
+        s->pend = s->plan_parents;
+        s->pend_segs = s->plan_segs;
+        s->pend_tiles = s->plan_tiles;
+        s->pend_elems = s->plan_elems;
+        s->plan_two_level = false;
+        s->plan_segs.clear();
+        s->plan_fused.clear();
+        s->plan_tiles.clear();
+        return 0;
+    }
     // L1: unsplit leaves of this level are only valid in the current buffer -- read them first
     if (s->criterion == B200DT_L1) CKR(l1_leaf_medians(ctx, s, s->median_pending_cur));
     SegDev *d_segs;
@@ -1065,6 +1273,8 @@ int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64
     sg.exact = 0;
     sg.pstep = 1;
     sg.pside = 0;
+    sg.vstart = -1;
+    sg.vpad = 0;
     s->plan_segs.assign(1, sg);
     s->plan_tiles.clear();
     for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{0, t});

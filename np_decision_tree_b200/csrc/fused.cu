@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(256, 3) level_fused_kernel(
                     out.score2 = best.g2;
                     out.k = best.k == 0x7fffffff ? -1 : best.k;
                     out.f = f;
+                    out.ppos = -1;
+                    out.pad_ = 0;
                     partials[(int64_t)(sg.fbase + 2 * td.tin + side) * F_search + f] = out;
                 }
             }

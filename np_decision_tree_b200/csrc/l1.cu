@@ -555,6 +555,8 @@ __global__ void __launch_bounds__(256) l1_argmin_kernel(int64_t stride, int F, c
         out.score2 = -second;
         out.k = bk == 0x7fffffff ? -1 : bk;
         out.f = f;
+        out.ppos = -1;
+        out.pad_ = 0;
         partials[(int64_t)sg.pbase * F + f] = out;
     }
 }
@@ -676,6 +678,8 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
         sg.exact = (nd.n < 2 * WALK_CHUNK_MIN || s->force_exact[i] || l1_exact_env()) ? 1 : 0;
         sg.pstep = 1;
         sg.pside = 0;
+        sg.vstart = -1;
+        sg.vpad = 0;
         s->h_segs[i] = sg;
         max_n = std::max(max_n, nd.n);
         n_elems += nd.n;

@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
             out.score2 = best.g2;
             out.k = best.k == 0x7fffffff ? -1 : best.k;
             out.f = f;
+            out.ppos = -1;
+            out.pad_ = 0;
             partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
         }
     }
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             out.score2 = best.g2;
             out.k = best.k == 0x7fffffff ? -1 : best.k;
             out.f = f;
+            out.ppos = -1;
+            out.pad_ = 0;
             partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
         }
     }
@@ -340,6 +344,8 @@ __global__ void __launch_bounds__(256) l2_exact_kernel(LevelArgs a, const int *_
         out.score2 = best.g2;
         out.k = best.k == 0x7fffffff ? -1 : best.k;
         out.f = f;
+        out.ppos = -1;
+        out.pad_ = 0;
         partials[(int64_t)(sg.pbase + sg.pside) * a.F_search + f] = out;
     }
 }
@@ -377,6 +383,8 @@ __device__ __forceinline__ Partial partial_none() {
     b.score2 = -CUDART_INF;
     b.k = -1;
     b.f = 0;
+    b.ppos = -1;
+    b.pad_ = 0;
     return b;
 }
 
@@ -446,9 +454,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
         c.k = w.k;
         c.f = w.f + col_offset;
         c.exact = sg.exact;
-        c.pad = 0;
+        c.pad = w.ppos;   // position inside the parent's segment while the node's rows have not been moved
         if (w.k >= 0 && X) {
-            const int row = a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
+            const int row = sg.vstart >= 0 ? a.orders[(int64_t)w.f * a.col_stride + sg.vstart + w.ppos]
+                                           : a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
             c.threshold = X[(int64_t)row * ldx + w.f];  // one.py:104-105: a data value, not a midpoint
         }
         out[seg] = c;

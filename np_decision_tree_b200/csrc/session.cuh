@@ -21,6 +21,13 @@ struct HNode {
     // slots fp_base + 2 * tile + fp_side, tile < fp_np
     bool has_fused = false;
     int fp_base = 0, fp_np = 0, fp_side = 0;
+    int vstart = -1;   // >= 0: this node's rows still lie inside its parent's segment, which starts here
+};
+
+// A split node of the first level of a pair whose children are searched before any data moves (children.cu)
+struct PendParent {
+    int node;          // index into Session::nodes
+    int start, n, nleft;
 };
 
 struct Session {
@@ -59,6 +66,16 @@ struct Session {
     size_t next_partial_slots = 0;  // candidate slots the next level needs in total
     int64_t plan_elems = 0;
     bool exact_round_done = false;
+    // two levels per data movement (children.cu), B200DT_TWO_LEVEL
+    bool two_level = false;        // enabled for this session
+    bool plan_two_level = false;   // the plan just decided: search the children from the parents' order, move nothing yet
+    bool pending = false;          // the live nodes' rows still lie inside their parents' segments
+    std::vector<PendParent> plan_parents;   // parents of the plan being decided (same order as plan_segs)
+    std::vector<PendParent> pend;           // ... of the pending level
+    std::vector<SegDev> pend_segs;          // their binary-partition plan, kept for materialisation on a near tie
+    std::vector<TileDesc> pend_tiles;
+    int64_t pend_elems = 0;
+    u32 *d_mask_a = nullptr;                // side mask of the first level of the pair
     // L1 leaves whose median is still to be read from the y-order column: those that live in the
     // current order buffer (unsplit nodes) and those created by the partition being applied
     std::vector<int> median_pending_cur, median_pending_next;

@@ -24,6 +24,8 @@ struct SegDev {
     int exact;      // 1: searched by the sequential-order kernel
     int pstep;      // candidate slot j of this node is pbase + j * pstep + pside: (1, 0) for slots of
     int pside;      // its own; (2, side) when the fused level kernel scored it from its parent's tiles
+    int vstart;     // >= 0: the node's rows still lie inside its PARENT's segment, which starts here (two-level
+    int vpad;       // search: candidates then carry Partial::ppos); -1: [start, start+n) is physical
 };
 
 // One split node handed to the fused level kernel (partition + search of the children).
@@ -32,6 +34,15 @@ struct PlanSeg {
     int start, n, nleft;
     int fbase;                // candidate slot of (tile tin, side) = fbase + 2 * tin + side
     int score_l, score_r;     // 1: that child is searched by the parallel scan at the next level
+};
+
+// One parent of a level pair handed to the 4-way partition (children.cu)
+struct Plan4 {
+    int start, n;
+    int n_l;    // rows of the left child
+    int n_ll;   // rows of the left child's left child (0 if it was not split)
+    int n_rl;   // rows of the right child's left child
+    int pad;
 };
 
 struct TileDesc {
@@ -240,6 +251,15 @@ int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, i
                        int64_t col_stride, int F_store, int F_search, const PlanSeg *plan, const TileDesc *tiles,
                        int n_tiles, int64_t n_elems, const u32 *mask, u64 *status, u32 epoch, Partial *partials,
                        int variant);
+int launch_children_scan(b200dt_ctx *ctx, const int *ord, const double *ypay, int64_t col_stride, int F_search,
+                         const PlanSeg *plan, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
+                         u64 *status, u32 epoch, Partial *partials, int variant);
+int launch_mark_left_virtual(b200dt_ctx *ctx, const int *orders, int64_t col_stride, const int *marks /* [n][4] */,
+                             int n_marks, int max_span, const u32 *parent_mask, u32 *mask);
+int launch_partition4(b200dt_ctx *ctx, const int *orders_in, int *orders_out, const double *y_in, double *y_out,
+                      int64_t col_stride, int F_store, const void *d_plan4, const TileDesc *tiles, int n_tiles,
+                      int64_t n_elems, const u32 *mask_a, const u32 *mask_b, int64_t N, u32 *codes, u64 *status,
+                      u32 epoch);
 int launch_mul(b200dt_ctx *ctx, const double *a, const double *b, int64_t n, double *out);
 int launch_l2w_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles, int64_t n_elems,
                     u64 *status, u32 epoch, Partial *partials);

@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(256) l2w_exact_kernel(LevelArgs a, const int *
         out.score2 = best.g2;
         out.k = best.k == 0x7fffffff ? -1 : best.k;
         out.f = f;
+        out.ppos = -1;
+        out.pad_ = 0;
         partials[(int64_t)(sg.pbase + sg.pside) * a.F_search + f] = out;
     }
 }
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(256, 3) l2w_scan_stream_kernel(LevelArgs a, co
             out.score2 = best.g2;
             out.k = best.k == 0x7fffffff ? -1 : best.k;
             out.f = f;
+            out.ppos = -1;
+            out.pad_ = 0;
             partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
         }
     }

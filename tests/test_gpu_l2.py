@@ -218,3 +218,30 @@ def test_no_cpu_fallback_symbols():
         src = getattr(sys.modules[m], "__file__", "") or ""
         if src.endswith(".py"):
             assert "oracle" not in open(src).read().replace("no CPU fallback", ""), m
+
+
+# ---- optional two-levels-per-data-movement mode (csrc/children.cu, B200DT_TWO_LEVEL=1) -------------------
+@pytest.fixture
+def two_level_env(monkeypatch):
+    monkeypatch.setenv("B200DT_TWO_LEVEL", "1")   # read by the library at every fit
+
+
+@pytest.mark.parametrize("seed,n,F,depth,yr,v", [(11, 60000, 6, 8, None, 1), (12, 30000, 5, 9, 50.0, 1),
+                                                 (13, 40000, 4, 6, None, 2), (14, 5000, 3, 7, None, 1)])
+def test_two_level_mode_builds_the_same_tree(two_level_env, seed, n, F, depth, yr, v):
+    """Children searched from the parent's order + one 4-way partition per level pair: same tree as the oracle
+    (large nodes take the pair path, small ones fall back to single levels, near ties materialise first)."""
+    from np_decision_tree_b200.decision_tree import one
+    X, y = small_problem(seed, n, F, yr)
+    want = oracle.fit_l2(X, y, max_depth=depth, v=v, sort_kind="stable")
+    got = one.build_regression_tree(X, y, max_depth=depth, v=v)
+    assert_same_tree(got, want, what=f"two-level seed {seed}")
+
+
+def test_two_level_mode_duplicate_columns(two_level_env):
+    """Structural ties (identical columns) force the exact re-search on the second level of a pair."""
+    from np_decision_tree_b200.decision_tree import one
+    X, y = small_problem(15, 50000, 3)
+    X = np.concatenate([X, X], axis=1)
+    want = oracle.fit_l2(X, y, max_depth=6, sort_kind="stable")
+    assert_same_tree(one.build_regression_tree(X, y, max_depth=6), want)
