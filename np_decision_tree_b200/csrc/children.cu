@@ -43,38 +43,48 @@ __global__ void __launch_bounds__(256, 3) l2_children_scan_kernel(
         const int64_t cbase = (int64_t)f * col_stride + sg.start + off;
         const double *yp = ypay + cbase;
         const int *col = ord + cbase;
-        // ---- striped loads: y into shared memory; the side bits of striped row i are exactly the 32 positions
-        //      that lane i owns in blocked order, so lane i keeps ballot i
-        u32 mybits = 0;
-#pragma unroll 4
-        for (int i0 = 0; i0 < ST_ITEMS; i0 += 8) {
-            int r[8];
+        // ---- striped loads: y into shared memory ---------------------------------------------------------------
+        if (cnt == ST_TILE) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = (i0 + u) * 32 + lane;
+            for (int i = 0; i < ST_ITEMS; ++i) sy[i * 33 + lane] = __ldcs(yp + i * 32 + lane);
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < ST_ITEMS; ++i) {
+                const int e = i * 32 + lane;
+                sy[i * 33 + lane] = e < cnt ? __ldcs(yp + e) : 0.0;
+            }
+        }
+        // ---- side bits: the ballot of striped row i holds exactly the 32 positions lane i owns in blocked order.
+        //      Two rounds of 16 rows: all row ids of a round, then all their mask words, are in flight together
+        u32 mybits = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int r[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = (h * 16 + u) * 32 + lane;
                 r[u] = e < cnt ? ld_stream_i32(col + e) : -1;
-                sy[(i0 + u) * 33 + lane] = e < cnt ? __ldcs(yp + e) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const bool is_left = r[u] >= 0 && ((__ldg(mask + (r[u] >> 5)) >> (r[u] & 31)) & 1u);
-                const u32 b = __ballot_sync(FULL_MASK, is_left);
-                if (lane == i0 + u) mybits = b;
+            for (int u = 0; u < 16; ++u) r[u] = r[u] >= 0 ? (int)((__ldg(mask + (r[u] >> 5)) >> (r[u] & 31)) & 1u) : 0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const u32 b = __ballot_sync(FULL_MASK, r[u] != 0);
+                if (lane == h * 16 + u) mybits = b;
             }
         }
         __syncwarp();
         const int nmine = max(0, min(ST_ITEMS, cnt - lane * ST_ITEMS));   // positions of this lane inside the node
         const u32 vmask = nmine >= 32 ? 0xffffffffu : ((1u << nmine) - 1u);
         // ---- this lane's sums per side, then the exclusive prefixes across lanes and tiles -----------------
-        double sL = 0.0, sR = 0.0;
+        double sL = 0.0, sA = 0.0;
 #pragma unroll 8
         for (int j = 0; j < ST_ITEMS; ++j) {
             const double y = mine[j];   // (0 beyond the node)
-            if ((mybits >> j) & 1u)
-                sL += y;
-            else
-                sR += y;
+            sA += y;
+            sL += ((mybits >> j) & 1u) ? y : 0.0;
         }
+        const double sR = sA - sL;   // (rounding differs from a separate sum: approximate search only)
         const int cl = __popc(mybits & vmask);
         double iL = sL, iR = sR;
         int ic = cl;
@@ -94,96 +104,70 @@ __global__ void __launch_bounds__(256, 3) l2_children_scan_kernel(
         tile.r = shfl_d(iR, 31);
         const Carry3 pre = lookback3(status, (int64_t)f * n_tiles + ti, td.tin, epoch, tile, lane);
 
-        // ---- score every split position of both children --------------------------------------------------
+        // ---- score every split position of both children: one COMPACTED pass per side over the set bits of this
+        //      lane's side mask, so the inner body is the single-sided one of the streaming search (l2.cu) --------
         const int nL = sg.nleft, nR = sg.n - sg.nleft;
-        const double meanL = sg.total_l * rcp_fast1((double)max(nL, 1)), meanR = sg.total_r * rcp_fast1((double)max(nR, 1));
-        double SL = pre.l + (iL - sL), SR = pre.r + (iR - sR);   // sums before this lane's first position
-        int kL = pre.c + (ic - cl);                              // left rows before it = next left child position
         const int p0 = off + lane * ST_ITEMS;                    // parent position of this lane's first element
-        int kR = p0 - kL;
+        const int kL0 = pre.c + (ic - cl);                       // left rows before it = next left child position
         double m1L = -CUDART_INF, m2L = -CUDART_INF, sbL = 0.0, dbL = 0.0;
         double m1R = -CUDART_INF, m2R = -CUDART_INF, sbR = 0.0, dbR = 0.0;
         int kbL = 0x7fffffff, kbR = 0x7fffffff, pbL = -1, pbR = -1;
         const bool scoreL = sg.score_l != 0, scoreR = sg.score_r != 0;
-        if (VARIANT == 1 && sg.n <= (1 << 24)) {
-            // incremental (k+1) mean and (k+1)(n-1-k) per child, advanced only by that child's rows
-            double kmL = (double)(kL + 1) * meanL, denL = (double)(kL + 1) * (double)(nL - 1 - kL);
-            double ddL = (double)(nL - 2 * kL - 3);
-            double kmR = (double)(kR + 1) * meanR, denR = (double)(kR + 1) * (double)(nR - 1 - kR);
-            double ddR = (double)(nR - 2 * kR - 3);
-#pragma unroll 4
-            for (int j = 0; j < nmine; ++j) {
-                const double y = mine[j];
-                if ((mybits >> j) & 1u) {
-                    SL += y;
-                    if (scoreL && kL < nL - 1) {
-                        const double dev = SL - kmL;
-                        const double g = dev * dev * rcp_fast1(denL);
-                        m2L = fmax(m2L, fmin(m1L, g));
-                        if (g > m1L) {
-                            m1L = g;
-                            sbL = SL;
-                            dbL = dev;
-                            kbL = kL;
-                            pbL = p0 + j;
-                        }
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? !scoreL : !scoreR) continue;   // (warp-uniform)
+            const int nc = side == 0 ? nL : nR;
+            const double mean = (side == 0 ? sg.total_l : sg.total_r) * rcp_fast1((double)max(nc, 1));
+            double S = side == 0 ? pre.l + (iL - sL) : pre.r + (iR - sR);   // child sum before this lane
+            int k = side == 0 ? kL0 : p0 - kL0;                             // child position of its next row
+            u32 bits = (side == 0 ? mybits : ~mybits) & vmask;
+            double m1 = -CUDART_INF, m2 = -CUDART_INF, sb = 0.0, db = 0.0;
+            int kb = 0x7fffffff, pb = -1;
+            if (VARIANT == 1 && sg.n <= (1 << 24)) {
+                double km = (double)(k + 1) * mean, den = (double)(k + 1) * (double)(nc - 1 - k);
+                double dd = (double)(nc - 2 * k - 3);
+                while (bits) {
+                    const int j = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    S += mine[j];
+                    const double dev = S - km;
+                    const double g = k < nc - 1 ? dev * dev * rcp_fast1(den) : -CUDART_INF;   // not the child's last row
+                    m2 = fmax(m2, fmin(m1, g));
+                    if (g > m1) {
+                        m1 = g;
+                        sb = S;
+                        db = dev;
+                        kb = k;
+                        pb = p0 + j;
                     }
-                    kmL += meanL;
-                    denL += ddL;
-                    ddL -= 2.0;
-                    ++kL;
-                } else {
-                    SR += y;
-                    if (scoreR && kR < nR - 1) {
-                        const double dev = SR - kmR;
-                        const double g = dev * dev * rcp_fast1(denR);
-                        m2R = fmax(m2R, fmin(m1R, g));
-                        if (g > m1R) {
-                            m1R = g;
-                            sbR = SR;
-                            dbR = dev;
-                            kbR = kR;
-                            pbR = p0 + j;
-                        }
+                    km += mean;
+                    den += dd;
+                    dd -= 2.0;
+                    ++k;
+                }
+                db = fabs(db);
+            } else {
+                while (bits) {
+                    const int j = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    S += mine[j];
+                    double dev = 0.0;
+                    const double g = k < nc - 1 ? score_fast(S, k, nc, mean, VARIANT, dev) : -CUDART_INF;
+                    m2 = fmax(m2, fmin(m1, g));
+                    if (g > m1) {
+                        m1 = g;
+                        sb = S;
+                        db = dev;
+                        kb = k;
+                        pb = p0 + j;
                     }
-                    kmR += meanR;
-                    denR += ddR;
-                    ddR -= 2.0;
-                    ++kR;
+                    ++k;
                 }
             }
-            dbL = fabs(dbL);
-            dbR = fabs(dbR);
-        } else {
-            for (int j = 0; j < nmine; ++j) {
-                const double y = mine[j];
-                const bool L = (mybits >> j) & 1u;
-                double dev = 0.0, g = -CUDART_INF;
-                if (L) {
-                    SL += y;
-                    if (scoreL && kL < nL - 1) g = score_fast(SL, kL, nL, meanL, VARIANT, dev);
-                    m2L = fmax(m2L, fmin(m1L, g));
-                    if (g > m1L) {
-                        m1L = g;
-                        sbL = SL;
-                        dbL = dev;
-                        kbL = kL;
-                        pbL = p0 + j;
-                    }
-                    ++kL;
-                } else {
-                    SR += y;
-                    if (scoreR && kR < nR - 1) g = score_fast(SR, kR, nR, meanR, VARIANT, dev);
-                    m2R = fmax(m2R, fmin(m1R, g));
-                    if (g > m1R) {
-                        m1R = g;
-                        sbR = SR;
-                        dbR = dev;
-                        kbR = kR;
-                        pbR = p0 + j;
-                    }
-                    ++kR;
-                }
+            if (side == 0) {
+                m1L = m1; m2L = m2; sbL = sb; dbL = db; kbL = kb; pbL = pb;
+            } else {
+                m1R = m1; m2R = m2; sbR = sb; dbR = db; kbR = kb; pbR = pb;
             }
         }
         __syncwarp();  // sy is overwritten by the next tile
@@ -256,7 +240,7 @@ __global__ void __launch_bounds__(256) merge_codes_kernel(const u32 *__restrict_
 
 // 4-way stable partition of (row, y): classes LL | LR | RL | RR of every planned parent (Plan4), in that order.
 // Carry between tiles: the counts of LL, LR, RL (RR follows from the position), through lookback3.
-__global__ void __launch_bounds__(256, 4) partition4_kernel(const int *__restrict__ in, int *__restrict__ out,
+__global__ void __launch_bounds__(256, 3) partition4_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                             const double *__restrict__ y_in, double *__restrict__ y_out,
                                                             int64_t col_stride, const Plan4 *__restrict__ plan,
                                                             const TileDesc *__restrict__ tiles, int n_tiles,
