@@ -289,6 +289,16 @@ def run_b200(args):
                         "frac": round(ach / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
                         "alg_bytes_per_launch": p["alg_bytes"] / p["launches"],
                         "avg_launch_ms": p["ms"] / p["launches"]}
+            notes = {
+                "partition": "algorithmic bytes = SURVEY 8d's 9 B per (row, feature) (4 in + 1 side flag + 4 out); by design "
+                             "the kernel also moves the 8-byte y payload in and out (24 B per element, DESIGN.md section 3), "
+                             "which is what lets the split search stream instead of gather; traffic / 24 B accounting = "
+                             "0.5 of peak; its limiter is the L1->crossbar request port (one request per side-bit look-up)",
+                "l2_scan_search": "algorithmic bytes = SURVEY 8d's 12 B per (row, feature); the streaming kernel reads 8 B",
+                "sort_radix_pass": "4-byte keys + 4-byte row ids, 4 passes; bound by shared-memory work per key, not bytes",
+            }
+            if dom in notes:
+                roofline["note"] = notes[dom]
         cpu = None
         if world == 1 and not args.no_cpu:
             rows = args.cpu_rows
