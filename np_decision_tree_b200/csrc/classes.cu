@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
                                                                const TileDesc *__restrict__ tiles, int n_tiles, int F,
                                                                int C, int row_bits, const int *__restrict__ excl,
                                                                const int *__restrict__ tot, u64 *status, u32 epoch,
+                                                               unsigned long long *node_best,
                                                                CPart *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,6 +456,16 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
         double best = -CUDART_INF;
         int best_k = 0x7fffffff;
         if (CRIT == 0) {
+            // node_best[seg] = the largest EXACT score any tile of this node (any column) has produced so far.
+            // A candidate whose cheap fp32 upper bound is below it cannot be the node's argmax (strictly smaller
+            // exact score), so its two exact divisions are skipped; ties are never skipped.
+            const bool filter = node_best != nullptr;
+            const double bound = filter ? __longlong_as_double((long long)ld_relaxed_u64(node_best + td.seg)) : -1.0;
+            // float shadows of the two sums of squares that are >= the true values BY CONSTRUCTION: converted once per
+            // chunk rounding up, then advanced with round-up additions / subtractions of rounded-up / rounded-down
+            // terms; reciprocals of rounded-down counts, inflated by the approximation's 1-ulp error; round-up
+            // product and sum.  So `ub` is a rigorous upper bound of the fp64 score (just not a tight one)
+            float SLf = __ll2float_ru(SL), SRf = __ll2float_ru(SR);
             for (int j = 0; j < mine; ++j) {
                 const int c = (int)(my[j] >> row_bits);
                 const u64 w = pk[c * 32 + lane];
@@ -463,7 +474,19 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
                 SR -= 2ll * R - 1;
                 pk[c * 32 + lane] = (u64)(u32)(L + 1) | ((u64)(u32)(R - 1) << 32);
                 const int kk = off + my0 + j;
-                if (kk < n - 1) {
+                bool exact = kk < n - 1;
+                if (filter) {
+                    SLf = __fadd_ru(SLf, __int2float_ru(2 * L + 1));
+                    SRf = __fsub_ru(SRf, __int2float_rd(2 * R - 1));
+                    float rl, rr;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(__int2float_rd(kk + 1)));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(__int2float_rd(n - kk - 1)));
+                    rl = __fmul_ru(rl, 1.0000003f);   // rcp.approx: max relative error 2^-23
+                    rr = __fmul_ru(rr, 1.0000003f);
+                    const float ub = __fmaf_ru(SLf, rl, __fmul_ru(SRf, rr));
+                    exact = exact && (double)ub >= fmax(bound, best);
+                }
+                if (exact) {
                     // strategy.py:52-55: left_sq / left_count + right_sq / right_count, IEEE fp64
                     const double sc = __dadd_rn(div_counts((double)SL, (double)(kk + 1)),
                                                 div_counts((double)SR, (double)(n - kk - 1)));
@@ -518,6 +541,9 @@ __global__ void __launch_bounds__(256) class_score_lane_kernel(const u32 *__rest
             p.k = best_k;
             p.pad = 0;
             partials[(int64_t)f * n_tiles + ti] = p;
+            // scores are positive, so their bit patterns order like the values
+            if (CRIT == 0 && node_best && best_k != 0x7fffffff)
+                atomicMax(node_best + td.seg, (unsigned long long)__double_as_longlong(best));
         }
         __syncwarp();
     }
@@ -695,6 +721,12 @@ int class_next_epoch(b200dt_ctx *ctx) {
     }
     ctx->epoch += 1;
     return 0;
+}
+
+// B200DT_CLASS_NOFILTER=1: evaluate every gini candidate exactly (no node-wide running bound)
+bool class_nofilter_env() {
+    const char *e = getenv("B200DT_CLASS_NOFILTER");
+    return e && e[0] == '1';
 }
 
 int resident_grid(b200dt_ctx *ctx, const void *kern, size_t smem, int64_t work_warps) {
@@ -955,8 +987,13 @@ static int class_search(b200dt_ctx *ctx, CCand *d_out) {
         const TileDesc *a_tiles = d_tiles;
         const int *a_excl = d_excl, *a_tot = d_tot;
         int a_F = F, a_C = C, a_bits = row_bits;
+        unsigned long long *d_node_best = nullptr;
+        if (!patk && !class_nofilter_env()) {
+            CKR(scratch_get(ctx, SB_L1_E, (size_t)n_live * 8 + 64, (void **)&d_node_best));
+            CK(cudaMemsetAsync(d_node_best, 0, (size_t)n_live * 8, ctx->stream));   // +0.0: below every score
+        }
         void *args[] = {&d_ord, &stride, &a_segs, &a_tiles, &n_tiles, &a_F, &a_C, &a_bits, &a_excl, &a_tot, &d_status,
-                        &epoch, &d_part};
+                        &epoch, &d_node_best, &d_part};
         LaunchScope ls(ctx, KC_CLASS_SCORE, 4.0 * (double)elems * F);
         if (single_pass)
             CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));   // tiles wait on earlier tiles
