@@ -608,10 +608,14 @@ int launch_walk(b200dt_ctx *ctx, const int *orders, int64_t stride, int F, const
     const char *env = getenv("B200DT_L1_CHUNKS");
     if (max_n >= 2 * WALK_CHUNK_MIN) {
         // as many chunks as keep every (walk, chunk) resident at once: a second wave would double the time
+        // (with more walks than half the slots the GPU is full anyway: no chunking; this also keeps the 2-D
+        //  grids of the preparation kernels below the 65535 limit of gridDim.y)
         const int slots = ctx->sm_count * 32;
-        P = std::min(std::min(WALK_CHUNKS_MAX, max_n / WALK_CHUNK_MIN), std::max(2, slots / std::max(1, n_walks)));
+        P = std::min(std::min(WALK_CHUNKS_MAX, max_n / WALK_CHUNK_MIN), slots / std::max(1, n_walks));
+        if (P < 2) P = 1;
     }
     if (env) P = std::max(1, std::min(WALK_CHUNKS_MAX, atoi(env)));
+    if (n_walks > 65535) P = 1;
     while (P > 1 && (size_t)n_walks * P * words * 4 > ((size_t)8 << 30)) --P;
     u32 *gbm = nullptr;
     float *d_bounds = nullptr;

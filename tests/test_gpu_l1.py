@@ -92,6 +92,26 @@ def test_l1_fit_vs_oracle(l1, n, F, depth, seed, yr):
     assert_same_tree(t, oracle.fit_l1(X, y, max_depth=depth, sort_kind="stable"), what=f"{n}x{F}")
 
 
+@pytest.mark.parametrize("n,F,depth,seed,yr", [(150000, 6, 3, 21, None),    # several chunked nodes per level
+                                                (80000, 4, 2, 22, 5.0),       # repeated targets: exact cost ties -> exact re-search
+                                                (70000, 3, 2, 23, None)])
+def test_l1_large_nodes_chunked_walks_and_costs(l1, n, F, depth, seed, yr):
+    """Nodes >= 32768 rows: the median walks run as concurrent chunks started from selected order statistics and
+    the cost sums are chunked (near ties fall back to the sequential sums): same tree as the oracle."""
+    X, y = small_problem(seed, n, F, yr, informative=2)
+    t = l1.l1.build_regression_tree_v2(X, y, max_depth=depth)
+    assert_same_tree(t, oracle.fit_l1(X, y, max_depth=depth, sort_kind="stable"), what=f"{n}x{F} depth {depth}")
+
+
+def test_l1_exact_env_matches(l1, monkeypatch):
+    X, y = small_problem(24, 90000, 4, None, informative=2)
+    a = l1.l1.build_regression_tree_v2(X, y, max_depth=2)
+    monkeypatch.setenv("B200DT_L1_EXACT", "1")
+    monkeypatch.setenv("B200DT_L1_CHUNKS", "1")
+    b = l1.l1.build_regression_tree_v2(X, y, max_depth=2)
+    assert_same_tree(a, b, what="chunked vs sequential L1")
+
+
 def test_l1_leaf_rule_quirk(l1):
     """strategy_l1.py:158,188: a node is a leaf when its best children COST is < min_improvement,
     so every 2-row node is a leaf (cost 0) and other nodes split down to single rows."""
