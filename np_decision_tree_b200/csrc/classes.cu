@@ -798,6 +798,7 @@ static int class_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, 
     if (criterion != B200DT_GINI && criterion != B200DT_P_AT_1) return ctx->fail_msg("fit_classes: unknown criterion");
     if (C < 1 || C > 32 * MAX_CLASS_CHUNKS) return ctx->fail_msg("fit_classes: n_classes must be in [1, 256]");
     if (N > (1ll << 26)) return ctx->fail_msg("fit_classes: N must be <= 2^26 (exact integer class statistics)");
+    if (F > 65535) return ctx->fail_msg("fit_classes: at most 65535 columns per GPU (shard the columns over more ranks)");
     if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit_classes: max_depth out of range [0, 30]");
     if (col_offset < 0 || col_offset + F > F_global) return ctx->fail_msg("fit_classes: column slice out of range");
     int row_bits = 1;

@@ -140,6 +140,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
                               const double *last_col, int64_t last_col_ld, const double *weight = nullptr) {
     if (N <= 0 || F_local <= 0) return ctx->fail_msg("fit: empty input");
     if (N >= (1ll << 30)) return ctx->fail_msg("fit: N must be < 2^30");
+    if (F_local > 65534) return ctx->fail_msg("fit: at most 65534 columns per GPU (shard the columns over more ranks)");
     if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit: max_depth out of range [0, 30]");
     if (criterion != B200DT_L2 && criterion != B200DT_L1) return ctx->fail_msg("fit: unknown criterion");
     session_free(ctx);

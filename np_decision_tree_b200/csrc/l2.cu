@@ -527,7 +527,7 @@ int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials
                     bool flat_rule) {
     if (a.n_segs <= 0) return 0;
     const Partial *stage1 = nullptr;
-    if (max_records > 64 * 1024 && sliced) {
+    if (max_records > 64 * 1024 && sliced && a.n_segs <= 65535) {   // (gridDim.y limit; deeper levels have small nodes)
         LaunchScope ls(ctx, KC_FINALIZE, 0.0);
         if (flat_rule)
             finalize_slices_kernel<true><<<dim3(FIN_SLICES, a.n_segs), 128, 0, ctx->stream>>>(a, partials, sliced);
