@@ -83,13 +83,21 @@ __global__ void __launch_bounds__(256) col_minmax_kernel(const double *__restric
     const int ncols = min(PREP_COLS, fb - cg * PREP_COLS);
     const int tcol = tid & (PREP_COLS - 1), trow = tid >> 3;
     u64 lo = ~0ull, hi = 0ull;
-    for (int64_t r = (int64_t)blockIdx.x * 32 + trow; r < N; r += (int64_t)gridDim.x * 32) {
-        if (tcol < ncols) {
-            const double x = X[r * ldx + cg * PREP_COLS + tcol];
-            if (x == x && fabs(x) != CUDART_INF) {
-                const u64 k = sortable_key(x);
-                lo = k < lo ? k : lo;
-                hi = k > hi ? k : hi;
+    // four rows in flight per thread (one load per iteration left the memory system idle)
+    const int64_t step = (int64_t)gridDim.x * 32;
+    if (tcol < ncols) {
+        const double *base = X + cg * PREP_COLS + tcol;
+        for (int64_t r = (int64_t)blockIdx.x * 32 + trow; r < N; r += 4 * step) {
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = (r + u * step < N) ? base[(r + u * step) * ldx] : CUDART_NAN;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (x[u] == x[u] && fabs(x[u]) != CUDART_INF) {
+                    const u64 k = sortable_key(x[u]);
+                    lo = k < lo ? k : lo;
+                    hi = k > hi ? k : hi;
+                }
             }
         }
     }
@@ -180,9 +188,11 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
             }
         }
         __syncthreads();
-        if (r0 + tid < N) {
-            for (int j = 0; j < ncols; ++j)
-                keys[(int64_t)(cg * PREP_COLS + j) * kstride + r0 + tid] = tile[j * PREP_PITCH + tid];
+        for (int rr = tid; rr < PREP_ROWS; rr += 256) {
+            if (r0 + rr < N) {
+                for (int j = 0; j < ncols; ++j)
+                    keys[(int64_t)(cg * PREP_COLS + j) * kstride + r0 + rr] = tile[j * PREP_PITCH + rr];
+            }
         }
         __syncthreads();
     }
