@@ -208,8 +208,19 @@ __global__ void __launch_bounds__(256) gather_payload_kernel(const int *__restri
                                                              const double *__restrict__ y, double *__restrict__ ypay,
                                                              int64_t col_stride, int64_t N) {
     const int64_t cbase = (int64_t)blockIdx.y * col_stride;
-    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < N; j += (int64_t)gridDim.x * 256)
-        ypay[cbase + j] = __ldg(y + ld_stream_i32(orders + cbase + j));
+    const int64_t step = (int64_t)gridDim.x * 256;
+    // four independent (row id -> y) chains in flight per thread
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < N; j += 4 * step) {
+        int r[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = (j + u * step < N) ? ld_stream_i32(orders + cbase + j + u * step) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = r[u] >= 0 ? __ldg(y + r[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r[u] >= 0) __stcs(ypay + cbase + j + u * step, v[u]);
+    }
 }
 
 }  // namespace
