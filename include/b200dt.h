@@ -252,6 +252,14 @@ int b200dt_rows_minmax(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, co
 int b200dt_rows_threshold_counts(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n,
                                  const int32_t *cols, int n_cols, const double *thresholds,
                                  int64_t *out_counts);
+/* regression with random thresholds (strategy.random_split_v2, ref strategy.py:136-146): register the float64
+ * targets once, then per node: sum of y and row count left of every threshold (masks.T.dot(y), masks.sum(0)) and
+ * out_node = {sum, min, max} of y over the node (np.mean for the leaf, np.unique(y).size <= 1 for base.py:16).
+ * Floating-point sums, accumulated in no fixed order (the reference's go through BLAS). */
+int b200dt_rows_set_targets(b200dt_ctx *ctx, const double *y, int space);
+int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, const int32_t *cols,
+                               int n_cols, const double *thresholds, double *out_sums,
+                               int64_t *out_counts, double *out_node);
 int b200dt_rows_split(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, int32_t col,
                       double threshold, int64_t *n_left);
 int b200dt_rows_end(b200dt_ctx *ctx);

@@ -80,6 +80,8 @@ _SIGNATURES = {
     "b200dt_rows_begin": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
     "b200dt_rows_minmax": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
     "b200dt_rows_threshold_counts": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
+    "b200dt_rows_set_targets": (c_int, [c_vp, c_vp, c_int]),
+    "b200dt_rows_threshold_sums": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200dt_rows_split": (c_int, [c_vp, c_int, c_i64, c_i64, ctypes.c_int32, c_dbl, ctypes.POINTER(c_i64)]),
     "b200dt_rows_end": (c_int, [c_vp]),
     "b200dt_profile_enable": (c_int, [c_vp, c_int]),

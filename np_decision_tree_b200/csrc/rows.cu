@@ -28,6 +28,7 @@ struct RowSession {
     int F = 0, C = 0;
     const double *dX = nullptr;
     const int *dlab = nullptr;
+    const double *dy = nullptr;   // regression targets (b200dt_rows_set_targets)
     int *rows[2] = {nullptr, nullptr};
 };
 
@@ -131,6 +132,94 @@ __global__ void __launch_bounds__(256) rows_columns_kernel(const double *__restr
         // shared layout is [class][column] (consecutive threads = consecutive columns: no bank conflicts)
         for (int i = threadIdx.x; i < n_cols * C; i += 256)
             if (sh[i]) atomicAdd(counts + (size_t)(i % n_cols) * C + i / n_cols, (unsigned long long)sh[i]);
+    }
+}
+
+// regression: per column, sum of y and number of the node's rows with x <= threshold; plus the node's own
+// sum / min / max of y (accumulated by the threads of column slot 0).
+// The sums are floating point, so their ORDER matters for one thing: two columns whose thresholds cut off the same
+// rows must get bit-identical sums (the reference's BLAS product sums every column in the same row order, ties
+// exactly and np.argmax takes the first).  So every thread sums its fixed share of the rows in list order into a
+// partial slot, and a second kernel adds the slots in slot order: the order depends on the rows only, never on
+// the column.
+__global__ void __launch_bounds__(256) rows_sums_kernel(const double *__restrict__ X, int64_t ldx,
+                                                        const int *__restrict__ rows, int64_t n,
+                                                        const int *__restrict__ cols, int n_cols, int cw,
+                                                        const double *__restrict__ y, const double *__restrict__ thr,
+                                                        double *__restrict__ psum, int *__restrict__ pcnt,
+                                                        double *__restrict__ pnode) {
+    const int tx = threadIdx.x % cw, ty = threadIdx.x / cw, rpb = 256 / cw;
+    const int64_t step = (int64_t)gridDim.x * rpb;
+    const int64_t slot = (int64_t)blockIdx.x * rpb + ty;
+    for (int c0 = 0; c0 < n_cols; c0 += cw) {
+        const int ci = c0 + tx;
+        const bool has_col = ci < n_cols;
+        const int col = has_col ? cols[ci] : 0;
+        const double t = has_col ? thr[ci] : 0.0;
+        const bool node_stats = ci == 0;
+        double s = 0.0, ns = 0.0, lo = CUDART_INF, hi = -CUDART_INF;
+        int c = 0;
+        for (int64_t r = (int64_t)blockIdx.x * rpb + ty; r < n; r += 4 * step) {
+            int row[4];
+            double x[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) row[u] = (r + u * step < n) ? rows[r + u * step] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[u] = (row[u] >= 0 && has_col) ? X[(int64_t)row[u] * ldx + col] : CUDART_NAN;
+                yv[u] = (row[u] >= 0 && has_col) ? y[row[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (x[u] <= t) {   // strategy.py:138: masks = X <= thresholds (NaN compares false)
+                    s += yv[u];
+                    ++c;
+                }
+                if (node_stats && row[u] >= 0) {
+                    ns += yv[u];
+                    lo = fmin(lo, yv[u]);
+                    hi = fmax(hi, yv[u]);
+                }
+            }
+        }
+        if (has_col) {
+            psum[slot * n_cols + ci] = s;
+            pcnt[slot * n_cols + ci] = c;
+        }
+        if (node_stats) {
+            pnode[slot * 3] = ns;
+            pnode[slot * 3 + 1] = lo;
+            pnode[slot * 3 + 2] = hi;
+        }
+    }
+}
+
+// slots are added in slot order; thread per column, thread 0 of block 0 also reduces the node statistics
+__global__ void __launch_bounds__(256) rows_sums_reduce_kernel(const double *__restrict__ psum,
+                                                               const int *__restrict__ pcnt,
+                                                               const double *__restrict__ pnode, int64_t n_slots,
+                                                               int n_cols, double *__restrict__ res) {
+    const int ci = blockIdx.x * 256 + threadIdx.x;
+    if (ci < n_cols) {
+        double s = 0.0;
+        long long c = 0;
+        for (int64_t p = 0; p < n_slots; ++p) {
+            s += psum[p * n_cols + ci];
+            c += pcnt[p * n_cols + ci];
+        }
+        res[ci] = s;
+        reinterpret_cast<long long *>(res)[n_cols + ci] = c;
+    }
+    if (ci == 0) {
+        double ns = 0.0, lo = CUDART_INF, hi = -CUDART_INF;
+        for (int64_t p = 0; p < n_slots; ++p) {
+            ns += pnode[p * 3];
+            lo = fmin(lo, pnode[p * 3 + 1]);
+            hi = fmax(hi, pnode[p * 3 + 2]);
+        }
+        res[2 * n_cols] = ns;
+        res[2 * n_cols + 1] = lo;
+        res[2 * n_cols + 2] = hi;
     }
 }
 
@@ -384,6 +473,72 @@ int b200dt_rows_threshold_counts(b200dt_ctx *ctx, int buffer, int64_t start, int
     CK(cudaMemcpyAsync(h, d_counts, (size_t)n_cols * C * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < (size_t)n_cols * C; ++i) out_counts[i] = (int64_t)h[i];
+    return 0;
+}
+
+int b200dt_rows_set_targets(b200dt_ctx *ctx, const double *y, int space) {
+    if (!ctx) return 1;
+    RowSession *s = ctx->row_session;
+    if (!s) return ctx->fail_msg("rows: session not begun");
+    if (!y) return ctx->fail_msg("rows_set_targets: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (space == B200DT_HOST) {
+        double *buf;
+        CKR(scratch_get(ctx, SB_YW, (size_t)s->N * 8 + 64, (void **)&buf));
+        CK(cudaMemcpyAsync(buf, y, (size_t)s->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // the caller's array may be a temporary
+        s->dy = buf;
+    } else {
+        s->dy = y;
+    }
+    return 0;
+}
+
+int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, const int32_t *cols, int n_cols,
+                               const double *thresholds, double *out_sums, int64_t *out_counts, double *out_node) {
+    if (!ctx) return 1;
+    if (!cols || !thresholds || !out_sums || !out_counts || !out_node)
+        return ctx->fail_msg("rows_threshold_sums: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(rows_check_segment(ctx, buffer, start, n));
+    RowSession *s = ctx->row_session;
+    if (!s->dy) return ctx->fail_msg("rows_threshold_sums: no targets registered (b200dt_rows_set_targets)");
+    if (n < 1) return ctx->fail_msg("rows_threshold_sums: empty node");
+    int *d_cols;
+    double *d_thr;
+    CKR(rows_cols_upload(ctx, cols, n_cols, thresholds, &d_cols, &d_thr));
+    // result block: sums[n_cols] | counts[n_cols] (int64) | node sum | node min | node max
+    double *d_res;
+    const size_t words = (size_t)2 * n_cols + 3;
+    CKR(scratch_get(ctx, SB_RESULT, words * 8 + 64, (void **)&d_res));
+    const int cw = column_width(n_cols), rpb = 256 / cw;
+    // few slots: they are added serially by one thread per column (and the nodes of deep levels are small)
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 4 * rpb - 1) / (4 * rpb), (int64_t)ctx->sm_count * 4));
+    const int64_t n_slots = (int64_t)grid * rpb;
+    double *d_psum, *d_pnode;
+    int *d_pcnt;
+    CKR(scratch_get(ctx, SB_L1_A, (size_t)n_slots * n_cols * 8 + 64, (void **)&d_psum));
+    CKR(scratch_get(ctx, SB_L1_B, (size_t)n_slots * n_cols * 4 + 64, (void **)&d_pcnt));
+    CKR(scratch_get(ctx, SB_L1_C, (size_t)n_slots * 3 * 8 + 64, (void **)&d_pnode));
+    {
+        LaunchScope ls(ctx, KC_ROWS, 8.0 * (double)n * n_cols, 2);
+        rows_sums_kernel<<<grid, 256, 0, ctx->stream>>>(s->dX, s->ldx, s->rows[buffer] + start, n, d_cols, n_cols, cw, s->dy,
+                                                        d_thr, d_psum, d_pcnt, d_pnode);
+        rows_sums_reduce_kernel<<<(n_cols + 255) / 256, 256, 0, ctx->stream>>>(d_psum, d_pcnt, d_pnode, n_slots, n_cols, d_res);
+    }
+    CK(cudaGetLastError());
+    double *h;
+    CKR(pinned_get(ctx, PIN_RESULT, words * 8, (void **)&h));
+    CK(cudaMemcpyAsync(h, d_res, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long *hk = reinterpret_cast<const long long *>(h);
+    for (int i = 0; i < n_cols; ++i) {
+        out_sums[i] = h[i];
+        out_counts[i] = (int64_t)hk[n_cols + i];
+    }
+    out_node[0] = h[2 * n_cols];
+    out_node[1] = h[2 * n_cols + 1];
+    out_node[2] = h[2 * n_cols + 2];
     return 0;
 }
 

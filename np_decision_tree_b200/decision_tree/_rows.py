@@ -52,6 +52,21 @@ class RowSession:
                                                                  cols.size, thr.ctypes.data, out.ctypes.data))
         return out
 
+    def set_targets(self, y):
+        """Register the float64 regression targets (b200dt_rows_set_targets)."""
+        yp, ys, self._yk = _lib.as_arg(y, np.float64, "y")
+        self.ctx.check(self.ctx.lib.b200dt_rows_set_targets(self.ctx.handle, yp, ys))
+
+    def threshold_sums(self, buffer, start, n, cols, thresholds):
+        """(sum of y left of each threshold, rows left of it, (sum, min, max) of y over the node)."""
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        sums, counts, node = np.empty(cols.size), np.empty(cols.size, dtype=np.int64), np.empty(3)
+        self.ctx.check(self.ctx.lib.b200dt_rows_threshold_sums(self.ctx.handle, buffer, start, n, cols.ctypes.data,
+                                                               cols.size, thr.ctypes.data, sums.ctypes.data,
+                                                               counts.ctypes.data, node.ctypes.data))
+        return sums, counts, node
+
     def split(self, buffer, start, n, col, threshold):
         n_left = ctypes.c_int64()
         self.ctx.check(self.ctx.lib.b200dt_rows_split(self.ctx.handle, buffer, start, n, int(col), float(threshold),
@@ -103,6 +118,66 @@ def grow_random(tree, X, labels, n_classes, max_depth, max_feature, min_improvem
                 raise _lib.B200Error("row split and threshold counts disagree")
             pending.append((start + n_left, n - n_left, buffer ^ 1, counts - left, node_id, False, depth + 1))
             pending.append((start, n_left, buffer ^ 1, left, node_id, True, depth + 1))
+    finally:
+        sess.close()
+    return tree
+
+
+def random_regression_node_search(sess, buffer, start, n, cols, surrogate, to_variance):
+    """One node of the regression ExtraTree (ref strategy.py:136-146, random_split_v2): thresholds from np.random,
+    left sums / counts from the GPU, the tiny surrogate + argmax in numpy like the reference.
+    Returns (index into cols, threshold, improvement, node y sum, node y min, node y max, rows left of the winner)."""
+    lo, hi = sess.minmax(buffer, start, n, cols)
+    thresholds = np.random.uniform(lo, hi)
+    left_sums, left_counts, node = sess.threshold_sums(buffer, start, n, cols, thresholds)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scores = surrogate(left_sums, left_counts, node[0], n)
+    best = int(np.argmax(scores))
+    return best, thresholds[best], to_variance(scores[best], n, node[0] / n), node, int(left_counts[best])
+
+
+def grow_random_regression(tree, X, y, max_depth, max_feature, min_improvement, min_sample_leaf, surrogate,
+                           to_variance):
+    """tree_builder.py:56-96 (build_tree) with split_method=random_split_v2 and leaf_from_data_regression."""
+    from .base import Task
+    ny = int(np.prod(y.shape))
+    sess = RowSession(X, np.zeros(ny, dtype=np.int32) if not (hasattr(y, "is_cuda") and y.is_cuda)
+                      else __import__("torch").zeros(ny, dtype=__import__("torch").int32, device=y.device), 1)
+    try:
+        sess.set_targets(y)
+        all_cols = np.arange(sess.F)
+        first = np.array([0], dtype=np.int32)
+        pending = [(0, sess.N, 0, None, True, 0)]
+        while pending:
+            start, n, buffer, parent, is_left, depth = pending.pop()
+            node_id = tree.new_node_from_task(Task(None, parent, is_left, depth))
+            if n == 0:   # an empty child (every row went to the other side): np.mean([]) in the reference
+                tree.add_leaf(node_id, np.nan)
+                continue
+            stop = n <= 2 * min_sample_leaf or depth >= max_depth
+            node = None
+            if not stop:
+                cols = all_cols if all_cols.size <= max_feature else np.random.permutation(all_cols)[:max_feature]
+                # base.py:16: a node whose targets are all equal is a leaf -- known from the node's min / max,
+                # which the search returns; the reference tests it BEFORE drawing, so look first
+                _, _, node = sess.threshold_sums(buffer, start, n, first, np.array([np.inf]))
+                if node[1] == node[2]:
+                    stop = True
+                else:
+                    best, threshold, improvement, node, n_left_expected = random_regression_node_search(
+                        sess, buffer, start, n, cols, surrogate, to_variance)
+                    stop = improvement < min_improvement
+            if stop:
+                if node is None:
+                    _, _, node = sess.threshold_sums(buffer, start, n, first, np.array([np.inf]))
+                tree.add_leaf(node_id, node[0] / n)       # leaf_from_data_regression: np.mean (tree_builder.py:16-17)
+                continue
+            tree.add_binary_v2(node_id, cols[best], threshold)
+            n_left = sess.split(buffer, start, n, cols[best], threshold)
+            if n_left != n_left_expected:
+                raise _lib.B200Error("row split and threshold counts disagree")
+            pending.append((start + n_left, n - n_left, buffer ^ 1, node_id, False, depth + 1))
+            pending.append((start, n_left, buffer ^ 1, node_id, True, depth + 1))
     finally:
         sess.close()
     return tree

@@ -10,8 +10,9 @@ precision-at-1 surrogate of every split position, flat argmax -- runs on the GPU
 ``random_classify`` / ``random_classify_p_at_k`` (strategy.py:149-172) draw one threshold per column
 from numpy's GLOBAL generator; the draw stays on the host (same ``np.random.uniform`` call, so a seeded
 run reproduces the reference), the column min / max and the class counts left of the thresholds come
-from the GPU (csrc/rows.cu).  The regression-side random splitters (``random_split``,
-``random_split_v2``) are not accelerated.
+from the GPU (csrc/rows.cu).  ``random_split_v2`` (strategy.py:136-146) is the regression counterpart: the
+GPU returns the sum of y and the row count left of every threshold.  ``random_split`` (rank-based cuts through
+a per-node argsort, strategy.py:174-185) is not accelerated.
 """
 import ctypes
 
@@ -29,6 +30,22 @@ def surrogate_to_p_at_k(value, y):
 def surrogate_to_gini(value, y):
     """strategy.py:107-108."""
     return value / y.shape[0] - np.sum(np.square(y.sum(axis=0) / y.sum()))
+
+
+def surrogate_variance_improvements(left_sums, left_counts, total_sums=None, total_count=None):
+    """strategy.py:4-27: sum_left^2 / n_left + sum_right^2 / n_right for every candidate.  With two arguments the
+    last row holds the totals."""
+    if total_sums is None:
+        left_sums, total_sums = left_sums[:-1], left_sums[-1]
+    if total_count is None:
+        left_counts, total_count = left_counts[:-1], left_counts[-1]
+    return (np.square(left_sums) / left_counts
+            + np.square(total_sums - left_sums) / (total_count - left_counts))
+
+
+def surrogate_to_variance(value, total_count, y_mean):
+    """strategy.py:28-29."""
+    return value / total_count - np.square(y_mean)
 
 
 def surrogate_gini_improvements(left_class_counts, left_counts, total_class_counts=None, total_count=None):
@@ -124,14 +141,30 @@ def random_classify_p_at_k(X, y, k=1):
     return _random_search(X, y, surrogate_p_at_k_improvements, _p_at_k_from_counts)
 
 
+def random_split_v2(X, y, cal_improvements=None):
+    """strategy.py:136-146: one U(min, max) threshold per column (np.random), best column by variance reduction.
+    ``cal_improvements`` is unused in the reference as well."""
+    from ._rows import RowSession, random_regression_node_search
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if np.asarray(X).shape[0] < 1:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    sess = RowSession(X, np.zeros(y.shape[0], dtype=np.int32), 1)
+    try:
+        sess.set_targets(y)
+        best, thr, improvement, _, _ = random_regression_node_search(
+            sess, 0, 0, sess.N, np.arange(sess.F), surrogate_variance_improvements, surrogate_to_variance)
+        return best, thr, improvement, np.zeros(sess.F, dtype=bool)
+    finally:
+        sess.close()
+
+
 def _not_accelerated(name):
     def fn(*args, **kwargs):
         raise NotImplementedError(
-            f"{name} (regression with random cuts) is not part of the accelerated path; the classification "
-            "splitters random_classify / random_classify_p_at_k and the exhaustive searches are")
+            f"{name} (rank-based random cuts) is not part of the accelerated path; random_split_v2, "
+            "random_classify / random_classify_p_at_k and the exhaustive searches are")
     fn.__name__ = name
     return fn
 
 
 random_split = _not_accelerated("random_split")
-random_split_v2 = _not_accelerated("random_split_v2")

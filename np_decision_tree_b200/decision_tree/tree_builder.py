@@ -43,6 +43,46 @@ _RANDOM = {random_classify: (_strategy.surrogate_gini_improvements, _strategy._g
            random_classify_p_at_k: (_strategy.surrogate_p_at_k_improvements, _strategy._p_at_k_from_counts)}
 
 
+def build_tree(X, y,
+               max_depth=2,
+               max_feature=100,
+               min_improvement=0.01,
+               min_sample_leaf=1,
+               split_method=None,
+               leaf_from_data=leaf_from_data_regression):
+    """tree_builder.py:56-96.  Regression trees with random thresholds: ``split_method=random_split_v2`` (the
+    reference's default here, ``greedy_split``, is the exhaustive MSE search that ``decision_tree.one`` supersedes:
+    use ``one.build_regression_tree``).  One-hot ``y`` with a classification splitter is routed to
+    ``build_classification_tree``."""
+    if split_method in _CRITERION or split_method in _RANDOM:
+        yy = np.asarray(y)
+        if yy.ndim != 2:
+            raise ValueError("classification splitters take the one-hot (n, C) targets build_classification_tree makes")
+        return build_classification_tree(X, np.argmax(yy, axis=1), max_depth, max_feature, min_improvement,
+                                         min_sample_leaf, split_method, leaf_from_data_classification, yy.shape[1])
+    if split_method is not random_split_v2:
+        raise NotImplementedError("build_tree: split_method must be this module's random_split_v2 (or a classification "
+                                  "splitter with one-hot y); for the exhaustive MSE search use one.build_regression_tree")
+    if leaf_from_data is not leaf_from_data_regression:
+        raise NotImplementedError("regression leaves are the node mean (leaf_from_data_regression)")
+    from ._rows import grow_random_regression
+    return grow_random_regression(DecisionTree(2 ** (max_depth + 1)), X, y, int(max_depth), int(max_feature),
+                                  float(min_improvement), int(min_sample_leaf), _strategy.surrogate_variance_improvements,
+                                  _strategy.surrogate_to_variance).final()
+
+
+def build_regression_tree(X, y,
+                          max_depth=2,
+                          max_feature=100,
+                          min_improvement=0.01,
+                          min_sample_leaf=1,
+                          split_method=random_split,
+                          leaf_from_data=leaf_from_data_regression):
+    """tree_builder.py:138-146.  (The reference's default ``random_split`` is not accelerated: pass
+    ``split_method=random_split_v2``.)"""
+    return build_tree(X, y, max_depth, max_feature, min_improvement, min_sample_leaf, split_method, leaf_from_data)
+
+
 def build_classification_tree(X, y,
                               max_depth=2,
                               max_feature=100,

@@ -43,4 +43,6 @@ from .np_tree_oracle import (  # noqa: F401
     fit_classes,
     random_class_split_node,
     fit_classes_random,
+    random_l2_split_node,
+    fit_l2_random,
 )

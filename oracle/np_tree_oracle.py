@@ -633,3 +633,60 @@ def fit_classes_random(X, labels, n_classes, max_depth=2, max_feature=100, min_i
         pending.append((rows[~goes_left], node, False, depth + 1))
         pending.append((rows[goes_left], node, True, depth + 1))
     return tree
+
+
+# --------------------------------------------------------------------------
+# regression with random thresholds (ExtraTree style)   
+# --------------------------------------------------------------------------
+def random_l2_split_node(X_node, y_node, rng=np.random):
+    """(column, threshold, improvement) of one node, one random threshold per column.
+
+    ref: decision_tree/strategy.py:136-146 (random_split_v2) with
+    surrogate_variance_improvements (:4-27, four-argument form) and
+    surrogate_to_variance (:28-29).  ``masks.T.dot(y)`` goes through BLAS in the
+    reference: the sums are only defined up to floating-point summation order.
+    """
+    n = X_node.shape[0]
+    thresholds = rng.uniform(X_node.min(axis=0), X_node.max(axis=0))
+    goes_left = X_node <= thresholds
+    left_sum = goes_left.T.astype(np.float64) @ y_node
+    n_left = goes_left.sum(axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        score = np.square(left_sum) / n_left + np.square(y_node.sum() - left_sum) / (n - n_left)
+    best = int(np.argmax(score))
+    return best, thresholds[best], score[best] / n - np.square(np.mean(y_node))
+
+
+def fit_l2_random(X, y, max_depth=2, max_feature=100, min_improvement=0.01, min_sample_leaf=1, rng=np.random):
+    """ref: decision_tree/tree_builder.py:56-96 (build_tree) with split_method=random_split_v2 and the default
+    leaf_from_data_regression (np.mean, :16-17); leaf rules of base.py:13-21 (rows <= 2 * min_sample_leaf, or
+    all targets equal).  Consumes ``rng`` like the reference: per searched node, depth first, [column
+    permutation] then one uniform per column."""
+    X = np.asarray(X)
+    y = np.asarray(y, dtype=np.float64)
+    all_columns = np.arange(X.shape[1])
+    tree = TreeArrays(max_depth)
+    t = tree.tree_
+    pending = [(np.arange(X.shape[0]), -1, True, 0)]
+    while pending:
+        rows, parent, is_left, depth = pending.pop()
+        tree.max_node_ += 1
+        node = tree.max_node_
+        if parent >= 0:
+            (t.children_left if is_left else t.children_right)[parent] = node
+        Xn, yn = X[rows], y[rows]
+        leaf = rows.size <= 2 * min_sample_leaf or np.unique(yn).size <= 1 or depth >= max_depth
+        if not leaf:
+            columns = all_columns if all_columns.size <= max_feature else rng.permutation(all_columns)[:max_feature]
+            best, threshold, improvement = random_l2_split_node(Xn[:, columns], yn, rng)
+            f = columns[best]
+            leaf = improvement < min_improvement
+        if leaf:
+            t.value[node] = np.mean(yn)
+            continue
+        t.feature[node] = f
+        t.threshold[node] = threshold
+        goes_left = Xn[:, f] <= threshold
+        pending.append((rows[~goes_left], node, False, depth + 1))
+        pending.append((rows[goes_left], node, True, depth + 1))
+    return tree

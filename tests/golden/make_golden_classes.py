@@ -86,6 +86,23 @@ def main():
             warnings.simplefilter("ignore")
             col, thr, imp, _ = RANDOM[crit](X, np.eye(C)[labels])
         out[f"rc_{name}_root"] = np.array([col, thr, imp], dtype=np.float64)
+    # ---- regression with random thresholds (strategy.py:136-146 under tree_builder.build_tree) ---------------
+    from make_golden import small_problem
+    for name, seed, n, F, depth, max_feature, kw in [("x0", 100, 400, 6, 5, 6, dict(min_improvement=1e-6)),
+                                                     ("x1", 101, 2000, 12, 9, 5, dict(min_improvement=1e-6)),
+                                                     ("x2", 102, 300, 4, 6, 4, dict(min_improvement=0.5, min_sample_leaf=8))]:
+        X, y = small_problem(seed, n, F)
+        np.random.seed(2000 + seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = tree_builder.build_tree(X, y, max_depth=depth, max_feature=max_feature,
+                                        split_method=strategy.random_split_v2, **kw)
+        out.update({f"rx_{name}_X": X, f"rx_{name}_y": y, f"rx_{name}_depth": np.int64(depth),
+                    f"rx_{name}_max_feature": np.int64(max_feature), f"rx_{name}_seed": np.int64(2000 + seed),
+                    f"rx_{name}_min_improvement": np.float64(kw.get("min_improvement", 0.01)),
+                    f"rx_{name}_min_sample_leaf": np.int64(kw.get("min_sample_leaf", 1))})
+        out.update(tree_dict(f"rx_{name}_", t))
+        out[f"rx_{name}_pred"] = utils.inference(X, t)
     np.savez_compressed(os.path.join(HERE, "reference_classes.npz"), **out)
     print("reference_classes.npz", os.path.getsize(os.path.join(HERE, "reference_classes.npz")), "bytes",
           {k[:-9]: int(out[k]) + 1 for k in out if k.endswith("_max_node")})

@@ -144,7 +144,13 @@ def test_classification_mirror_rejects_what_is_not_accelerated():
     with pytest.raises(NotImplementedError, match="split_method"):
         tree_builder.build_classification_tree(X, y, split_method=strategy.random_split)   # regression splitter
     with pytest.raises(NotImplementedError, match="random cuts"):
-        strategy.random_split_v2(X, y)
+        strategy.random_split(X, y)                                        # rank-based cuts: not accelerated
+    with pytest.raises(NotImplementedError, match="random_split_v2"):
+        tree_builder.build_regression_tree(X, y.astype(float))             # reference default: random_split
+    assert strategy.surrogate_to_variance(8.0, 4, 1.0) == 1.0
+    ls = np.array([1.0, 3.0])
+    assert np.array_equal(strategy.surrogate_variance_improvements(ls, np.array([1, 2]), 6.0, 3),
+                          np.square(ls) / np.array([1, 2]) + np.square(6.0 - ls) / np.array([2, 1]))
     with pytest.raises(NotImplementedError, match="max_feature"):
         tree_builder.build_classification_tree(X, y, max_feature=3, split_method=strategy.greedy_classification)
     with pytest.raises(IndexError):

@@ -225,3 +225,72 @@ def test_estimator_wrapper_cross_val():
         scores = cross_val_score(Mree(max_depth=8, max_feature=mf, max_classes=3, split_method=method), X, labels,
                                  cv=3, scoring=scorer)
         assert scores.shape == (3,) and scores.min() > 0.5, (method.__name__, scores)
+
+
+# ---- regression with random thresholds (random_split_v2 under build_tree; csrc/rows.cu) --------------------
+@pytest.mark.parametrize("name", ["x0", "x1", "x2"])
+def test_random_regression_tree_matches_reference_golden(golden_classes, mods, name):
+    """Structure and thresholds exact under the same seed; leaf means to 1e-9 (floating-point sums: the
+    reference's go through BLAS, ours through atomics)."""
+    strategy, tree_builder, utils = mods
+    g, p = golden_classes, f"rx_{name}_"
+    np.random.seed(int(g[p + "seed"]))
+    t = tree_builder.build_tree(g[p + "X"], g[p + "y"], max_depth=int(g[p + "depth"]),
+                                max_feature=int(g[p + "max_feature"]), min_improvement=float(g[p + "min_improvement"]),
+                                min_sample_leaf=int(g[p + "min_sample_leaf"]), split_method=strategy.random_split_v2)
+    assert_same_tree(t, GoldenTree(g, p), leaf_rtol=1e-9, what=name)
+    np.testing.assert_allclose(utils.inference(g[p + "X"], t), g[p + "pred"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed,n,F,depth,max_feature,msl", [(71, 30000, 16, 10, 16, 100), (72, 4000, 200, 8, 30, 50)])
+def test_random_regression_tree_matches_oracle(mods, seed, n, F, depth, max_feature, msl):
+    """Nodes stop at 2 * msl rows: in nodes of a handful of rows two columns can cut COMPLEMENTARY row sets, whose
+    scores are mathematically equal; which one wins then hangs on the last bit of the reference's BLAS dot product
+    and pairwise y.sum(), which no other summation order reproduces."""
+    from util import small_problem
+    strategy, tree_builder, utils = mods
+    X, y = small_problem(seed, n, F, None, informative=4)
+    kw = dict(max_depth=depth, max_feature=max_feature, min_improvement=1e-6, min_sample_leaf=msl)
+    np.random.seed(seed)
+    want = oracle.fit_l2_random(X, y, **kw)
+    np.random.seed(seed)
+    got = tree_builder.build_regression_tree(X, y, split_method=strategy.random_split_v2, **kw)
+    assert_same_tree(got, want, leaf_rtol=1e-9, what=f"random regression seed {seed}")
+
+
+def test_random_regression_deep_tree_quality(mods):
+    """Down to single rows the tree may differ from the oracle's on tied candidates only: same size class, same fit."""
+    from util import small_problem
+    strategy, tree_builder, utils = mods
+    X, y = small_problem(71, 30000, 16, None, informative=4)
+    kw = dict(max_depth=10, max_feature=16, min_improvement=1e-6)
+    np.random.seed(71)
+    want = oracle.fit_l2_random(X, y, **kw)
+    np.random.seed(71)
+    got = tree_builder.build_regression_tree(X, y, split_method=strategy.random_split_v2, **kw)
+    mse_w = np.mean((oracle.predict(X, want) - y) ** 2)
+    mse_g = np.mean((utils.inference(X, got) - y) ** 2)
+    assert abs(got.max_node_ + 1 - want.node_count) <= 0.05 * want.node_count
+    assert mse_g == pytest.approx(mse_w, rel=0.05)
+    top = slice(0, 16)   # the first nodes (large) are identical
+    assert np.array_equal(got.tree_.feature[top], want.tree_.feature[top])
+    assert np.array_equal(got.tree_.threshold[top], want.tree_.threshold[top])
+
+
+def test_random_split_v2_single_node(mods):
+    from util import small_problem
+    strategy, _, _ = mods
+    X, y = small_problem(73, 5000, 7)
+    np.random.seed(11)
+    wf, wthr, wimp = oracle.random_l2_split_node(X, y)
+    np.random.seed(11)
+    f, thr, imp, const = strategy.random_split_v2(X, y)
+    assert (f, thr) == (wf, wthr) and imp == pytest.approx(wimp, rel=1e-9)
+    assert const.shape == (7,) and not const.any()
+
+
+def test_random_regression_constant_targets_is_a_leaf(mods):
+    strategy, tree_builder, _ = mods
+    X = np.random.RandomState(0).standard_normal((100, 3))
+    t = tree_builder.build_tree(X, np.full(100, 2.5), max_depth=3, split_method=strategy.random_split_v2)
+    assert t.max_node_ == 0 and t.tree_.value[0] == 2.5

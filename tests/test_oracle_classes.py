@@ -81,3 +81,16 @@ def test_oracle_random_root_search_matches_reference(golden_classes, name):
     want = golden_classes[f"rc_{name}_root"]
     assert f == int(want[0]) and thr == want[1]
     assert imp == want[2] or (np.isnan(imp) and np.isnan(want[2]))
+
+
+# ---- regression with random thresholds (random_split_v2 under build_tree) ------------------------------------
+@pytest.mark.parametrize("name", ["x0", "x1", "x2"])
+def test_oracle_random_regression_tree_matches_reference(golden_classes, name):
+    g, p = golden_classes, f"rx_{name}_"
+    np.random.seed(int(g[p + "seed"]))
+    t = oracle.fit_l2_random(g[p + "X"], g[p + "y"], max_depth=int(g[p + "depth"]),
+                             max_feature=int(g[p + "max_feature"]), min_improvement=float(g[p + "min_improvement"]),
+                             min_sample_leaf=int(g[p + "min_sample_leaf"]))
+    # structure / thresholds exact (thresholds are np.random draws); leaf means: same numpy expression here
+    assert_same_tree(t, GoldenTree(g, p), leaf_rtol=1e-12, what=name)
+    np.testing.assert_allclose(oracle.predict(g[p + "X"], t), g[p + "pred"], rtol=1e-12)
