@@ -148,9 +148,11 @@ __global__ void __launch_bounds__(256) rows_sums_kernel(const double *__restrict
                                                         const double *__restrict__ y, const double *__restrict__ thr,
                                                         double *__restrict__ psum, int *__restrict__ pcnt,
                                                         double *__restrict__ pnode) {
+    __shared__ double s_sum[256], s_ns[256], s_lo[256], s_hi[256];
+    __shared__ int s_cnt[256];
     const int tx = threadIdx.x % cw, ty = threadIdx.x / cw, rpb = 256 / cw;
     const int64_t step = (int64_t)gridDim.x * rpb;
-    const int64_t slot = (int64_t)blockIdx.x * rpb + ty;
+    const int64_t slot = blockIdx.x;   // one partial slot per block: its row groups are combined below, in order
     for (int c0 = 0; c0 < n_cols; c0 += cw) {
         const int ci = c0 + tx;
         const bool has_col = ci < n_cols;
@@ -182,15 +184,36 @@ __global__ void __launch_bounds__(256) rows_sums_kernel(const double *__restrict
                 }
             }
         }
-        if (has_col) {
-            psum[slot * n_cols + ci] = s;
-            pcnt[slot * n_cols + ci] = c;
-        }
+        s_sum[threadIdx.x] = s;
+        s_cnt[threadIdx.x] = c;
         if (node_stats) {
-            pnode[slot * 3] = ns;
-            pnode[slot * 3 + 1] = lo;
-            pnode[slot * 3 + 2] = hi;
+            s_ns[ty] = ns;
+            s_lo[ty] = lo;
+            s_hi[ty] = hi;
         }
+        __syncthreads();
+        if (ty == 0 && has_col) {   // row groups in group order: the order depends on the rows only
+            double bs = 0.0;
+            int bc = 0;
+            for (int g = 0; g < rpb; ++g) {
+                bs += s_sum[g * cw + tx];
+                bc += s_cnt[g * cw + tx];
+            }
+            psum[slot * n_cols + ci] = bs;
+            pcnt[slot * n_cols + ci] = bc;
+            if (node_stats) {
+                double bn = 0.0, bl = CUDART_INF, bh = -CUDART_INF;
+                for (int g = 0; g < rpb; ++g) {
+                    bn += s_ns[g];
+                    bl = fmin(bl, s_lo[g]);
+                    bh = fmax(bh, s_hi[g]);
+                }
+                pnode[slot * 3] = bn;
+                pnode[slot * 3 + 1] = bl;
+                pnode[slot * 3 + 2] = bh;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -514,7 +537,7 @@ int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64
     const int cw = column_width(n_cols), rpb = 256 / cw;
     // few slots: they are added serially by one thread per column (and the nodes of deep levels are small)
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 4 * rpb - 1) / (4 * rpb), (int64_t)ctx->sm_count * 4));
-    const int64_t n_slots = (int64_t)grid * rpb;
+    const int64_t n_slots = (int64_t)grid;
     double *d_psum, *d_pnode;
     int *d_pcnt;
     CKR(scratch_get(ctx, SB_L1_A, (size_t)n_slots * n_cols * 8 + 64, (void **)&d_psum));

@@ -1,6 +1,6 @@
 """Side measurements of the other BASELINE.json configs (bench.py carries only the headline, C4).
 
-    python scripts/bench_configs.py [c2] [c3] [c5] [cls] [--cpu]
+    python scripts/bench_configs.py [c2] [c3] [c5] [cls] [rreg] [--cpu]
 
 C2: make_regression 10 000 x 100, L2 depth 10 fit + inference (README.md:60-64: 390 ms reference)
 C3: L1 build_regression_tree_v2 depth 1, 1 M x 100 (cummedian path; BASELINE.md: 138 s on one core)
@@ -165,5 +165,50 @@ if "cls" in args:
         out["cls"]["cpu_port"] = {"sample": f"{n_s} x {f_s}", "fit_s": dt, "rows_features_per_s": n_s * f_s / dt,
                                   "nodes": o.node_count, "gpu_tree_identical": bool(same)}
     del X, labels
+
+if "rreg" in args:
+    # regression ExtraTree (strategy.random_split_v2 under tree_builder.build_tree), depth 10, device-resident
+    from np_decision_tree_b200.decision_tree import strategy, tree_builder
+    N = int(os.environ.get("CLS_ROWS", 10_000_000))
+    F = int(os.environ.get("CLS_FEATURES", 256))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    X = torch.empty((N, F), dtype=torch.float64, device="cuda")
+    for c0 in range(0, F, 32):
+        X[:, c0:c0 + 32] = torch.randn((N, min(32, F - c0)), dtype=torch.float64, device="cuda", generator=g)
+    cols = torch.arange(0, 250, 25, device="cuda")
+    y = (X[:, cols] * torch.linspace(10, 100, 10, dtype=torch.float64, device="cuda")).sum(1)
+    kw = dict(max_depth=10, max_feature=F, min_improvement=1e-6, split_method=strategy.random_split_v2)
+    np.random.seed(0)
+    tree_builder.build_tree(X, y, **kw)
+    ctx = _lib.default_context(0)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    np.random.seed(0)
+    t_fit, tree = best_of(lambda: tree_builder.build_tree(X, y, **kw), n=3)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    pred = utils.inference(X[:1_000_000], tree)
+    out["rreg"] = {"rows": N, "features": F, "fit_ms_device_in": t_fit * 1e3, "rows_features_per_s": N * F / t_fit,
+                   "nodes": tree.max_node_ + 1,
+                   "train_mse_1M": float(((torch.as_tensor(pred, device="cuda") - y[:1_000_000]) ** 2).mean()),
+                   "y_variance": float(y[:1_000_000].var()),
+                   "kernels_ms_per_fit": {k: round(v["ms"] / 3, 3) for k, v in prof.items() if v["launches"]}}
+    if with_cpu:
+        import oracle
+        n_s, f_s = 100_000, min(F, 32)
+        Xc, yc = X[:n_s, :f_s].cpu().numpy(), y[:n_s].cpu().numpy()
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        o = oracle.fit_l2_random(Xc, yc, max_depth=10, max_feature=f_s, min_improvement=1e-6, min_sample_leaf=50)
+        dt = time.perf_counter() - t0
+        np.random.seed(0)
+        gt = tree_builder.build_tree(Xc, yc, max_depth=10, max_feature=f_s, min_improvement=1e-6, min_sample_leaf=50,
+                                     split_method=strategy.random_split_v2)
+        same = all(np.array_equal(getattr(gt.tree_, k), getattr(o.tree_, k))
+                   for k in ("children_left", "children_right", "feature", "threshold"))
+        out["rreg"]["cpu_port"] = {"sample": f"{n_s} x {f_s}", "fit_s": dt, "rows_features_per_s": n_s * f_s / dt,
+                                   "nodes": o.node_count, "gpu_tree_identical": bool(same)}
+    del X, y
 
 print(json.dumps(out, indent=1))
