@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200tree.so")
-SOURCES = ["sort.cu", "l2.cu", "fused.cu", "weighted.cu", "partition.cu", "children.cu", "predict.cu", "l1.cu", "classes.cu", "rows.cu", "fit.cu"]
+SOURCES = ["sort.cu", "l2.cu", "weighted.cu", "partition.cu", "relabel.cu", "children.cu", "predict.cu", "l1.cu", "classes.cu", "rows.cu", "fit.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-Wno-maybe-uninitialized", "--expt-relaxed-constexpr",

@@ -37,6 +37,7 @@ enum KernelClass {
     KC_CLASS_SCORE,       // classification: gini / precision-at-1 scores + argmax
     KC_ROWS,              // random-threshold splitters: column min/max, threshold counts, row-list split
     KC_CHILD_SCAN,        // two-level search: both children scored from the parent's order (side-bit look-up)
+    KC_RELABEL,           // once per fit: contiguous row ids per node (relabel.cu)
     KC_COUNT
 };
 
@@ -44,7 +45,7 @@ static const char *const kKernelClassNames[KC_COUNT] = {
     "sort_prepare", "sort_radix_pass", "l2_scan_search", "l2_exact_search", "finalize_argbest",
     "mark_left_rows", "partition", "predict", "l1_rank", "l1_median_descent", "l1_cost_search",
     "misc", "level_fused_partition_search", "gather_y_payload", "sort_fixup_ties", "class_tile_histogram",
-    "class_score_search", "row_list_ops", "l2_children_scan_search"};
+    "class_score_search", "row_list_ops", "l2_children_scan_search", "relabel_rows"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -120,7 +121,7 @@ enum ScratchId {
     SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
     SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
     SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
-    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_MASK_A, SB_CODES, SB_PLAN4, SB_COUNT
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_MASK_A, SB_CODES, SB_PLAN4, SB_NEWID, SB_ROWMAP, SB_RL_BINS, SB_RL_COUNTS, SB_COUNT
 };
 
 static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {
@@ -253,6 +254,16 @@ __device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
+}
+
+// Bulk-async prefetch of [p, p + bytes) into L2 (one instruction per tile instead of DRAM latency on the
+// critical path of the warp that streams it later).  The address is rounded down and the size up to 16 B;
+// the few extra bytes stay inside the buffer (callers keep >= 16 B of slack).
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, u32 bytes) {
+    const u64 a = (u64)p;
+    const u64 a0 = a & ~15ull;
+    const u32 n = (u32)((a - a0) + bytes + 15u) & ~15u;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
 }
 
 // relaxed / acquire-release accesses for the look-back flag words

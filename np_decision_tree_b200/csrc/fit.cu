@@ -233,10 +233,13 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     int64_t kcap = 0;
     int payload_cols_done = 0;
     {
-        const char *e = getenv("B200DT_FUSE");
-        s->fuse_levels = e && e[0] == '1';
         const char *t = getenv("B200DT_TWO_LEVEL");
         s->two_level = t && t[0] == '1';
+        // rows whose side bits stay L1-resident (1.5 M rows = 183 KB of mask); B200DT_RELABEL_ROWS overrides
+        // (0 = off; small values make small test problems take the relabelled path)
+        s->relabel_window = 1500000;
+        const char *w = getenv("B200DT_RELABEL_ROWS");
+        if (w && w[0]) s->relabel_window = atoll(w);
     }
     if (criterion == B200DT_L2) {
         // y-payload double buffer; idle during the sort, so it doubles as the radix key scratch
@@ -409,6 +412,7 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     a.segs = s->d_segs;
     a.n_segs = n_live;
     a.wpay = s->wpay[s->cur];
+    a.row_map = s->relabeled ? s->d_rowmap : nullptr;
     int64_t max_records = 0;
     for (const SegDev &sg : s->h_segs) max_records = std::max<int64_t>(max_records, (int64_t)sg.np * s->F_local);
     Partial *d_sliced;
@@ -501,11 +505,10 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     s->next_fused_slots = 0;
     s->plan_parents.clear();
     s->plan_two_level = false;
-    const bool payload = s->ypay[0] != nullptr && s->fuse_levels && !s->dw;
     // two levels per data movement (children.cu): this level's children may be searched from the parents' order
     // (first level of a pair), or the live nodes already are such children (second level: `was_pending`)
     const bool was_pending = s->pending;
-    const bool pair_candidate = s->two_level && !was_pending && !payload && s->ypay[0] != nullptr && !s->dw &&
+    const bool pair_candidate = s->two_level && !was_pending && s->ypay[0] != nullptr && !s->dw &&
                                 s->criterion == B200DT_L2;
     std::vector<PlanSeg> pair_plan;        // one per plan seg, filled while the plan is built
     std::vector<int> pair_children;        // (left child, right child) node ids per plan seg
@@ -589,29 +592,6 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
                 pair_children.push_back(lc);
                 pair_children.push_back(rc);
             }
-            if (payload) {
-                // the fused level kernel scores the children that the next level searches by scan
-                PlanSeg ps;
-                ps.total_l = w.left_sum;
-                ps.total_r = total - w.left_sum;
-                ps.start = start;
-                ps.n = n;
-                ps.nleft = nl;
-                ps.fbase = s->next_fused_slots;
-                ps.score_l = ps.score_r = 0;
-                for (int c : {lc, rc}) {
-                    HNode &ch = s->nodes[c];
-                    if (!ch.leaf && ch.n > EXACT_MAX_ROWS) {
-                        ch.has_fused = true;
-                        ch.fp_base = ps.fbase;
-                        ch.fp_np = sg.np;
-                        ch.fp_side = c == lc ? 0 : 1;
-                        (c == lc ? ps.score_l : ps.score_r) = 1;
-                    }
-                }
-                s->next_fused_slots += 2 * sg.np;
-                s->plan_fused.push_back(ps);
-            }
             const int fl = w.f - s->col_offset;
             if (fl >= 0 && fl < s->F_local) {  // this rank owns the winning column: it marks the left rows
                 const HNode &me = s->nodes[nid];
@@ -631,6 +611,16 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
                 }
             }
         }
+    }
+    // relabel the rows with this partition?  Once, at the first level whose children all fit the window;
+    // payload sessions only (no kernel gathers y or weights by row id there).  Every rank of a sharded fit
+    // takes the same decision from the same plan.
+    s->plan_relabel = false;
+    if (!s->relabeled && !s->two_level && s->ypay[0] != nullptr && s->relabel_window > 0 &&
+        s->N > s->relabel_window && !s->plan_segs.empty() && s->plan_segs.size() <= 512) {
+        int64_t largest = 0;
+        for (int c : next_live) largest = std::max<int64_t>(largest, s->nodes[c].n);
+        s->plan_relabel = largest <= s->relabel_window;
     }
     if (!s->plan_segs.empty()) {
         *need_partition = 1;
@@ -830,26 +820,37 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
     CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64, s->plan_tiles.data(), s->plan_tiles.size(), d_tiles));
     u32 *ticket = (u32 *)((char *)ctx->scratch[SB_MASK].p + (size_t)((s->N + 31) / 32) * 4);
     u64 *pstatus;
-    if (s->ypay[0] && s->fuse_levels && !s->dw && s->plan_fused.size() == s->plan_segs.size()) {
-        // streaming path: partition (row, y) and search the children in the same pass
-        PlanSeg *d_plan;
-        const size_t plan_bytes = s->plan_fused.size() * sizeof(PlanSeg);
-        CKR(scratch_get(ctx, SB_PLAN, plan_bytes + 64, (void **)&d_plan));
-        CKR(upload(ctx, PIN_PLAN, mark_bytes + seg_bytes + 64 + s->plan_tiles.size() * sizeof(TileDesc) + 64,
-                   s->plan_fused.data(), s->plan_fused.size(), d_plan));
-        CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 48, (void **)&pstatus, true));
-        CKR(scratch_get(ctx, SB_PARTIAL, (s->next_partial_slots + 1) * s->F_local * sizeof(Partial) + 64,
-                        (void **)&s->d_partials));
-        CKR(next_epoch(ctx));
-        CKR(launch_level_fused(ctx, s->ord[s->cur], s->ypay[s->cur], s->ord[s->cur ^ 1], s->ypay[s->cur ^ 1],
-                               s->col_stride, s->F_store, s->F_local, d_plan, d_tiles, (int)s->plan_tiles.size(),
-                               s->plan_elems, d_mask, pstatus, ctx->epoch, s->d_partials, s->variant));
-    } else {
-        CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
-        CKR(next_epoch(ctx));
-        CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
-                             (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket,
-                             s->ypay[s->cur], s->ypay[s->cur ^ 1], s->wpay[s->cur], s->wpay[s->cur ^ 1]));
+    CKR(scratch_get(ctx, SB_STATUS_P, (s->plan_tiles.size() * (size_t)s->F_store + 1) * 8, (void **)&pstatus, true));
+    int *d_newid = nullptr;
+    if (s->plan_relabel) {
+        // new ids = the children's position ranges (relabel.cu); computed from the (reduced) side mask
+        const int n_segs = (int)s->plan_segs.size();
+        std::vector<int> bin_start(2 * (size_t)n_segs);
+        for (int i = 0; i < n_segs; ++i) {
+            bin_start[2 * i] = s->plan_segs[i].start;
+            bin_start[2 * i + 1] = s->plan_segs[i].start + s->plan_segs[i].nleft;
+        }
+        int *d_bin_start, *d_counts, *d_map;
+        unsigned short *d_bins;
+        const size_t off_bins = mark_bytes + seg_bytes + 64 + s->plan_tiles.size() * sizeof(TileDesc) + 64;
+        CKR(scratch_get(ctx, SB_NEWID, (size_t)s->N * 4 + 64, (void **)&d_newid));
+        CKR(scratch_get(ctx, SB_ROWMAP, (size_t)s->N * 4 + 64, (void **)&d_map));
+        CKR(scratch_get(ctx, SB_RL_BINS, (size_t)s->N * 2 + 64, (void **)&d_bins));
+        CKR(scratch_get(ctx, SB_RL_COUNTS, ((size_t)2 * n_segs * relabel_chunks(s->N) + 2 * (size_t)n_segs) * 4 + 64,
+                        (void **)&d_counts));
+        d_bin_start = d_counts + (size_t)2 * n_segs * relabel_chunks(s->N);
+        CKR(upload(ctx, PIN_PLAN, off_bins, bin_start.data(), bin_start.size(), d_bin_start));
+        CKR(launch_relabel(ctx, s->ord[s->cur], d_segs, n_segs, d_tiles, (int)s->plan_tiles.size(), d_mask, s->N,
+                           d_bin_start, d_bins, d_counts, d_newid, nullptr, d_map));
+        s->d_rowmap = d_map;
+    }
+    CKR(next_epoch(ctx));
+    CKR(launch_partition(ctx, s->ord[s->cur], s->ord[s->cur ^ 1], s->col_stride, s->F_store, d_segs, d_tiles,
+                         (int)s->plan_tiles.size(), s->plan_elems, d_mask, pstatus, ctx->epoch, ticket,
+                         s->ypay[s->cur], s->ypay[s->cur ^ 1], s->wpay[s->cur], s->wpay[s->cur ^ 1], 0, d_newid));
+    if (s->plan_relabel) {
+        s->relabeled = true;
+        s->plan_relabel = false;
     }
     s->cur ^= 1;
     s->plan_segs.clear();

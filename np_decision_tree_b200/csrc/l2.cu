@@ -182,6 +182,15 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
         const int off = td.tin * ST_TILE;
         const int cnt = min(ST_TILE, sg.n - off);
         const double *yp = a.ypay + (int64_t)f * a.col_stride + sg.start + off;
+        if (lane == 0 && t + stride_tiles < total_tiles) {
+            // this warp's NEXT tile -> L2, so its loads below do not wait on DRAM
+            const int64_t tn = t + stride_tiles;
+            const TileDesc tdn = tiles[tn / a.F_search];
+            const int nstart = a.segs[tdn.seg].start, nn = a.segs[tdn.seg].n;
+            const int offn = tdn.tin * ST_TILE;
+            prefetch_l2_bulk(a.ypay + (int64_t)(tn % a.F_search) * a.col_stride + nstart + offn,
+                             (u32)min(ST_TILE, nn - offn) * 8u);
+        }
         if (cnt == ST_TILE) {
 #pragma unroll
             for (int i = 0; i < ST_ITEMS; ++i) sy[i * 33 + lane] = __ldcs(yp + i * 32 + lane);
@@ -456,8 +465,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
         c.exact = sg.exact;
         c.pad = w.ppos;   // position inside the parent's segment while the node's rows have not been moved
         if (w.k >= 0 && X) {
-            const int row = sg.vstart >= 0 ? a.orders[(int64_t)w.f * a.col_stride + sg.vstart + w.ppos]
-                                           : a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
+            int row = sg.vstart >= 0 ? a.orders[(int64_t)w.f * a.col_stride + sg.vstart + w.ppos]
+                                     : a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
+            if (a.row_map) row = a.row_map[row];
             c.threshold = X[(int64_t)row * ldx + w.f];  // one.py:104-105: a data value, not a midpoint
         }
         out[seg] = c;

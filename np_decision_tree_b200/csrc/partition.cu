@@ -10,6 +10,9 @@
 // [start, start+nleft) and [start+nleft, start+n) of the output array, so every node of the
 // next level is again one segment shared by all columns.
 // Algorithmic bytes: 4 (row id in) + 1 (side flag) + 4 (row id out) = 9 per element.
+#include <algorithm>
+#include <cstdlib>
+
 #include "tree_kernels.cuh"
 
 namespace {
@@ -29,14 +32,17 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // One warp owns one tile of PT_TILE positions of one (node, column).  Every lane sees every
 // ballot, so the running left-count of the tile lives in registers: no shared memory, no
 // block barrier.  Persistent grid, static tile-major order (see l2.cu).
-template <int PAY>
+// RELABEL: this level also hands out the new, node-contiguous row ids (relabel.cu): the look-up reads the
+// row's new id instead of its side bit, the side is `new id < first id of the right child`, and the new id
+// is what gets written.
+template <int PAY, bool RELABEL, bool PREFETCH>
 __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                            const double *__restrict__ y_in, double *__restrict__ y_out,
                                                            const double *__restrict__ w_in, double *__restrict__ w_out,
                                                            int64_t col_stride, const SegDev *__restrict__ segs,
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
                                                            const u32 *__restrict__ mask, u64 *status, u32 epoch,
-                                                           int n_cols, int row_mask) {
+                                                           int n_cols, int row_mask, const int *__restrict__ newid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
     const int64_t total_tiles = (int64_t)n_tiles * n_cols;
@@ -49,6 +55,19 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         const int cnt = min(PT_TILE, sg.n - off);
         const int64_t cbase = (int64_t)f * col_stride + sg.start;
         const int *col = in + cbase + off;
+        if (PREFETCH && lane == 0 && t + stride_tiles < total_tiles) {
+            // this warp's NEXT tile: pull its row ids and payload into L2 while the current tile is processed
+            const int64_t tn = t + stride_tiles;
+            const int fn = (int)(tn % n_cols);
+            const TileDesc tdn = tiles[tn / n_cols];
+            const int nstart = segs[tdn.seg].start, nn = segs[tdn.seg].n;
+            const int offn = tdn.tin * PT_TILE;
+            const u32 cntn = (u32)min(PT_TILE, nn - offn);
+            const int64_t nb = (int64_t)fn * col_stride + nstart + offn;
+            prefetch_l2_bulk(in + nb, cntn * 4u);
+            if (PAY == 1 || PAY == 2) prefetch_l2_bulk(y_in + nb, cntn * 8u);
+            if (PAY == 2) prefetch_l2_bulk(w_in + nb, cntn * 8u);
+        }
         int rows[PT_ITEMS];
         if (cnt == PT_TILE) {
 #pragma unroll
@@ -63,7 +82,14 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
             // PAY == 3: the class id rides in the bits above row_mask (classes.cu), so the sign bit is data
             const int row = PAY == 3 ? (rows[i] & row_mask) : rows[i];
             const bool ok = PAY == 3 ? (i * 32 + lane < cnt) : (row >= 0);
-            const bool is_left = ok && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
+            bool is_left;
+            if (RELABEL) {
+                const int nid = ok ? __ldg(newid + row) : 0x7fffffff;
+                is_left = nid < sg.start + sg.nleft;   // the left child takes the ids [start, start + nleft)
+                rows[i] = nid;
+            } else {
+                is_left = ok && ((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u);
+            }
             leftbits |= (is_left ? 1u : 0u) << i;
         }
         // every lane sees every ballot, so the tile's left count is register arithmetic; the ballots
@@ -107,7 +133,37 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
     }
 }
 
+// y travelling with the row ids: ypay[f][j] = y[orders[f][j]] (once per fit, after the sort)
+__global__ void __launch_bounds__(256) gather_payload_kernel(const int *__restrict__ orders,
+                                                             const double *__restrict__ y, double *__restrict__ ypay,
+                                                             int64_t col_stride, int64_t N) {
+    const int64_t cbase = (int64_t)blockIdx.y * col_stride;
+    const int64_t step = (int64_t)gridDim.x * 256;
+    // four independent (row id -> y) chains in flight per thread
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < N; j += 4 * step) {
+        int r[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = (j + u * step < N) ? ld_stream_i32(orders + cbase + j + u * step) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = r[u] >= 0 ? __ldg(y + r[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r[u] >= 0) __stcs(ypay + cbase + j + u * step, v[u]);
+    }
+}
+
 }  // namespace
+
+int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, double *ypay, int64_t col_stride,
+                          int F_store, int64_t N) {
+    if (N <= 0 || F_store <= 0) return 0;
+    int gx = (int)std::min<int64_t>((N + 255) / 256, (int64_t)ctx->sm_count * 16 / std::max(1, std::min(F_store, 16)) + 1);
+    LaunchScope ls(ctx, KC_PAYLOAD, 20.0 * (double)N * F_store);
+    gather_payload_kernel<<<dim3((unsigned)gx, (unsigned)F_store), 256, 0, ctx->stream>>>(orders, y, ypay, col_stride, N);
+    CK(cudaGetLastError());
+    return 0;
+}
 
 int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, const int *marks, int n_marks,
                      int max_left, u32 *mask) {
@@ -127,15 +183,20 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                      u64 *status, u32 epoch, u32 *ticket, const double *y_in, double *y_out, const double *w_in,
-                     double *w_out, int packed_row_mask) {
+                     double *w_out, int packed_row_mask, const int *newid) {
     (void)ticket;
     if (n_tiles <= 0) return 0;
     const int pay = packed_row_mask ? 3 : (y_in && y_out) ? ((w_in && w_out) ? 2 : 1) : 0;
     const int64_t total = (int64_t)n_tiles * F_store;
     int per_sm = 0;
-    const void *kern = pay == 3 ? (const void *)partition_kernel<3>
-                       : pay == 2 ? (const void *)partition_kernel<2>
-                       : pay == 1 ? (const void *)partition_kernel<1> : (const void *)partition_kernel<0>;
+    if (newid && pay != 1 && pay != 2) return ctx->fail_msg("partition: row relabelling needs a payload session");
+    static const bool prefetch = !(getenv("B200DT_NO_PREFETCH") && getenv("B200DT_NO_PREFETCH")[0] == '1');
+    const void *kern = pay == 3 ? (const void *)partition_kernel<3, false, true>
+                       : pay == 2 ? (newid ? (const void *)partition_kernel<2, true, true> : (const void *)partition_kernel<2, false, true>)
+                       : pay == 1 ? (newid ? (const void *)partition_kernel<1, true, true>
+                                           : prefetch ? (const void *)partition_kernel<1, false, true>
+                                                      : (const void *)partition_kernel<1, false, false>)
+                                  : (const void *)partition_kernel<0, false, true>;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > (total + 7) / 8) grid = (total + 7) / 8;
@@ -143,7 +204,7 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
     const double *yi = (pay == 1 || pay == 2) ? y_in : nullptr, *wi = pay == 2 ? w_in : nullptr;
     double *yo = (pay == 1 || pay == 2) ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;
     void *args[] = {&orders_in, &orders_out, &yi, &yo, &wi, &wo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status,
-                    &epoch, &F_store, &packed_row_mask};
+                    &epoch, &F_store, &packed_row_mask, &newid};
     CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
     return 0;
 }

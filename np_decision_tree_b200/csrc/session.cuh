@@ -60,12 +60,17 @@ struct Session {
     std::vector<PlanSeg> plan_fused;   // same nodes, for the fused level kernel (payload sessions)
     std::vector<TileDesc> plan_tiles;
     int flags = 0;             // B200DT_NUMBER_BY_LEVEL | B200DT_LEAF_IF_LE (four.py conventions)
-    bool fuse_levels = false;  // B200DT_FUSE=1: partition + search of the children in one kernel (fused.cu)
     int fused_slots = 0;       // candidate slots of the CURRENT level written by the fused kernel
     int next_fused_slots = 0;  // ... of the level being planned
     size_t next_partial_slots = 0;  // candidate slots the next level needs in total
     int64_t plan_elems = 0;
     bool exact_round_done = false;
+    // row relabelling (relabel.cu): once per fit, at the first level whose children all fit an L1-resident
+    // window of the side mask, the partition hands out node-contiguous row ids
+    int64_t relabel_window = 0;      // rows; 0 = never relabel
+    bool plan_relabel = false;       // the plan just decided relabels
+    bool relabeled = false;
+    int *d_rowmap = nullptr;         // row id -> original row, once relabelled
     // two levels per data movement (children.cu), B200DT_TWO_LEVEL
     bool two_level = false;        // enabled for this session
     bool plan_two_level = false;   // the plan just decided: search the children from the parents' order, move nothing yet

@@ -286,10 +286,19 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
     const u32 lt = lanemask_lt();
     u32 rank[RS_ITEMS];
 #define RS_DIGIT(i) ((u32)(key[i] >> shift) & 255u)
+    // Peer masks from 8 ballots per item, NOT match.any: measured on B200 (scripts/ubench/rank_ubench.cu) one
+    // warp-wide MATCH.ANY costs ~61 SM cycles -- 150 G keys/s chip-wide, i.e. 17 ms of the 22 ms this pass took --
+    // while the ballot form ranks 330 G keys/s.
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        rank[i] = __match_any_sync(FULL_MASK, RS_DIGIT(i));
-        if (!full) rank[i] &= __ballot_sync(FULL_MASK, o0 + i * 32 < count);
+        const u32 d = RS_DIGIT(i);
+        u32 peers = full ? FULL_MASK : __ballot_sync(FULL_MASK, o0 + i * 32 < count);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const u32 v = __ballot_sync(FULL_MASK, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? v : ~v;
+        }
+        rank[i] = peers;
     }
     u32 *my_hist = sm.warp_hist[warp];
 #pragma unroll

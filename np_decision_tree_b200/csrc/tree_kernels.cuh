@@ -68,6 +68,7 @@ struct LevelArgs {
     const double *wpay;     // weighted fits: the sample weights travelling the same way (ypay then holds y*w)
     const SegDev *segs;
     int n_segs;
+    const int *row_map;     // non-null after the rows were relabelled (relabel.cu): row id -> ORIGINAL row
 };
 
 #ifdef __CUDACC__
@@ -247,10 +248,6 @@ __device__ __forceinline__ Carry3 lookback3(u64 *status, int64_t idx, int tin, u
 }
 #endif  // __CUDACC__
 
-int launch_level_fused(b200dt_ctx *ctx, const int *ord_in, const double *y_in, int *ord_out, double *y_out,
-                       int64_t col_stride, int F_store, int F_search, const PlanSeg *plan, const TileDesc *tiles,
-                       int n_tiles, int64_t n_elems, const u32 *mask, u64 *status, u32 epoch, Partial *partials,
-                       int variant);
 int launch_children_scan(b200dt_ctx *ctx, const int *ord, const double *ypay, int64_t col_stride, int F_search,
                          const PlanSeg *plan, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                          u64 *status, u32 epoch, Partial *partials, int variant);
@@ -283,4 +280,9 @@ int launch_mark_left(b200dt_ctx *ctx, const int *orders, int64_t col_stride, con
 int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int64_t col_stride, int F_store,
                      const SegDev *segs, const TileDesc *tiles, int n_tiles, int64_t n_elems, const u32 *mask,
                      u64 *status, u32 epoch, u32 *ticket, const double *y_in = nullptr, double *y_out = nullptr,
-                     const double *w_in = nullptr, double *w_out = nullptr, int packed_row_mask = 0);
+                     const double *w_in = nullptr, double *w_out = nullptr, int packed_row_mask = 0,
+                     const int *newid = nullptr);
+int launch_relabel(b200dt_ctx *ctx, const int *col, const SegDev *d_segs, int n_segs, const TileDesc *d_tiles,
+                   int n_tiles, const u32 *mask, int64_t N, const int *d_bin_start, unsigned short *d_bins,
+                   int *d_counts, int *d_newid, const int *d_map_old, int *d_map_new);
+int relabel_chunks(int64_t N);

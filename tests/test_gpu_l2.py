@@ -245,3 +245,36 @@ def test_two_level_mode_duplicate_columns(two_level_env):
     X = np.concatenate([X, X], axis=1)
     want = oracle.fit_l2(X, y, max_depth=6, sort_kind="stable")
     assert_same_tree(one.build_regression_tree(X, y, max_depth=6), want)
+
+
+# ---- row relabelling (csrc/relabel.cu): node-contiguous row ids, handed out by one partition ----------
+@pytest.mark.parametrize("window", [1, 700, 20000])
+@pytest.mark.parametrize("seed,n,F,depth,yr,v", [(21, 60000, 6, 9, None, 1), (22, 30000, 5, 10, 50.0, 1),
+                                                 (23, 40000, 4, 7, None, 2), (24, 5000, 3, 8, None, 1)])
+def test_relabelled_rows_build_the_same_tree(monkeypatch, window, seed, n, F, depth, yr, v):
+    """B200DT_RELABEL_ROWS makes these small problems relabel their rows (at the level whose children all
+    have <= `window` rows; window 1 never does, 20000 does at the top, 700 in the middle of the tree):
+    thresholds are fetched through the row map and the side masks use the new ids -- same tree."""
+    from np_decision_tree_b200.decision_tree import one
+    monkeypatch.setenv("B200DT_RELABEL_ROWS", str(window))
+    X, y = small_problem(seed, n, F, yr)
+    want = oracle.fit_l2(X, y, max_depth=depth, v=v, sort_kind="stable")
+    got = one.build_regression_tree(X, y, max_depth=depth, v=v)
+    assert_same_tree(got, want, what=f"relabel window {window} seed {seed}")
+
+
+def test_relabelled_rows_duplicate_columns_and_weights(monkeypatch):
+    """Structural ties after the relabelling (exact re-search on relabelled rows), and the weighted builder."""
+    from np_decision_tree_b200.decision_tree import one, four
+    monkeypatch.setenv("B200DT_RELABEL_ROWS", "9000")
+    X, y = small_problem(25, 50000, 3)
+    X2 = np.concatenate([X, X], axis=1)
+    assert_same_tree(one.build_regression_tree(X2, y, max_depth=8), oracle.fit_l2(X2, y, max_depth=8, sort_kind="stable"))
+    w = np.random.RandomState(26).uniform(0.25, 4.0, size=y.shape[0])
+    got = four.build_regression_tree(X, y, max_depth=7, weight=w)
+    monkeypatch.setenv("B200DT_RELABEL_ROWS", "0")
+    want = four.build_regression_tree(X, y, max_depth=7, weight=w)
+    for name in ("children_left", "children_right", "feature", "threshold", "n_node_samples"):
+        assert np.array_equal(getattr(got.tree_, name), getattr(want.tree_, name)), name
+    # node sums come out of a look-back scan whose grouping depends on timing: last bits may differ
+    np.testing.assert_allclose(got.tree_.value, want.tree_.value, rtol=RTOL)
