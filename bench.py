@@ -12,16 +12,24 @@ sharded over the ranks (strong scaling).
 
   value : N*F / t, inputs resident in HBM when the timed region starts (CUDA events on the
           launch stream, barrier + synchronize on both sides, max over ranks).
-  e2e   : the same fit through the public API with HOST (pinned) buffers -- every step copies
-          X and y host->device and the tree device->host inside the timed region.
+  e2e   : the same fit through the public API with HOST buffers -- every step copies X and y
+          host->device and the tree device->host inside the timed region.  Measured twice: with an
+          ordinary pageable numpy array (what a user of the reference passes; this is `e2e.value`)
+          and with a pinned buffer (`pinned_ms_per_step`).
+  inference : utils.inference of the depth-10 tree of the timed fit over 12 500 000 x F device-resident
+          rows PER GPU (row-sharded, no exchange; at 8 GPUs this is BASELINE.json configs[4],
+          100 M x 256), rows/s and the fraction of the HBM roofline on 32 B x path + 8 B per row.
+  tree_sha : SHA-256 over the five tree arrays up to max_node_ -- identical at every GPU count.
   roofline : the kernel class with the largest share of the step; achieved = algorithmic
           bytes / summed CUDA-event time of its launches in the timed
           region; peak = MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline : the oracle (numpy port of the reference, single thread like the reference)
           on a bounded row sample of the same generator, rank 0, N=1 only.
 
---impl reference times the reference's CPU algorithm (the oracle port; the Python reference
-itself cannot travel to the GPU box) on a bounded sample per step.
+--impl reference times the reference's CPU algorithm on a bounded sample per step: the oracle port
+(`kind: "port"`).  The reference is Python; its sources are never copied into this tree (not even
+into a git-ignored directory), so the unmodified reference itself only runs in the build container,
+where tests/golden/make_golden*.py use it to generate the fixtures the oracle is pinned to.
 """
 import argparse
 import json
@@ -51,10 +59,12 @@ def parse():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--features", type=int, default=256)
     ap.add_argument("--depth", type=int, default=10)
-    ap.add_argument("--cpu-rows", type=int, default=100_000, help="row sample of the CPU baseline")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="row sample of the CPU arms (0 = sized to the time budget)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--inference-rows", type=int, default=12_500_000, help="rows per GPU of the inference block")
     return ap.parse_args()
 
 
@@ -172,21 +182,35 @@ def cpu_fit_seconds(rows, F, depth, repeats=1):
     return best
 
 
+CPU_SECONDS_PER_ROW = 6.4e-5 / 256   # oracle port, per (row, feature) of a depth-10 fit (measured: 100 000 x 256 in 6.4 s)
+
+
+def reference_rows(args, fits):
+    """Rows of the CPU sample such that `fits` whole fits take about two minutes (50 000 ... 1 000 000)."""
+    if args.cpu_rows > 0:
+        return args.cpu_rows
+    rows = 120.0 / max(1, fits) / (CPU_SECONDS_PER_ROW * args.features)
+    return int(min(1_000_000, max(50_000, rows)) // 1000 * 1000)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows, F = args.cpu_rows, args.features
+    F = args.features
+    rows = reference_rows(args, args.steps + min(args.warmup, 1))
     import oracle
     X, y = gen_problem_numpy(rows, F)
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):     # numpy has nothing to warm up beyond the first touch of the buffers
         oracle.fit_l2(X, y, max_depth=args.depth)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oracle.fit_l2(X, y, max_depth=args.depth)
     dt = (time.perf_counter() - t0) / args.steps
     value = rows * F / dt
-    sample = f"{rows} x {F} rows sample of the same generator, whole depth-{args.depth} fit per step"
+    sample = (f"{rows} x {F} row sample of the same generator (sized so that {args.steps} fits take about two "
+              f"minutes), whole depth-{args.depth} fit per step, 1 of {os.cpu_count()} host cores (the reference is "
+              f"single-threaded numpy)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -259,6 +283,12 @@ def run_b200(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
     value = N * F / (ms_per_step * 1e-3)
+    tree_sha = tree_digest(tree)
+
+    # ---- inference of that tree, row-sharded, device-resident (BASELINE.json configs[4] at 8 GPUs) ----
+    inference = None
+    if not args.no_inference:
+        inference = measure_inference(args, torch, dist, ctx, tree, world, rank, dev, barrier)
 
     # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region ----
     e2e = None
@@ -275,10 +305,18 @@ def run_b200(args):
         for name, p in prof.items():
             per_step_ms = p["ms"] / args.steps
             ach = p["alg_bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 and p["alg_bytes"] > 0 else None
+            # bytes the launches of this class really moved in one step (ncu dram__bytes, 1-GPU capture of this
+            # workload; scaled by this rank's share of the columns)
+            traffic = ncu_traffic(name)
+            tr = None
+            if traffic and p["ms"] > 0:
+                tr = traffic * ((hi - lo) / F) / (per_step_ms * 1e-3) / 1e9
             kernels[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": p["launches"] / args.steps,
                              "share_of_step": round(per_step_ms / ms_per_step, 4),
                              "achieved_gbs": None if ach is None else round(ach, 1),
-                             "frac": None if ach is None else round(ach / peak, 4)}
+                             "frac_alg": None if ach is None else round(ach / peak, 4),
+                             "traffic_gbs": None if tr is None else round(tr, 1),
+                             "frac_traffic": None if tr is None else round(tr / peak, 4)}
         timed = {k: v for k, v in prof.items() if v["alg_bytes"] > 0}
         dom = max(timed, key=lambda k: timed[k]["ms"]) if timed else None
         roofline = None
@@ -286,22 +324,23 @@ def run_b200(args):
             p = prof[dom]
             ach = p["alg_bytes"] / (p["ms"] * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                        "frac": round(ach / peak, 4), "traffic": ncu_traffic(dom, per_launch=True), "peak_source": peak_src,
                         "alg_bytes_per_launch": p["alg_bytes"] / p["launches"],
                         "avg_launch_ms": p["ms"] / p["launches"]}
             notes = {
                 "partition": "algorithmic bytes = SURVEY 8d's 9 B per (row, feature) (4 in + 1 side flag + 4 out); by design "
                              "the kernel also moves the 8-byte y payload in and out (24 B per element, DESIGN.md section 3), "
-                             "which is what lets the split search stream instead of gather; traffic / 24 B accounting = "
-                             "0.5 of peak; its limiter is the L1->crossbar request port (one request per side-bit look-up)",
-                "l2_scan_search": "algorithmic bytes = SURVEY 8d's 12 B per (row, feature); the streaming kernel reads 8 B",
-                "sort_radix_pass": "4-byte keys + 4-byte row ids, 4 passes; bound by shared-memory work per key, not bytes",
+                             "which is what lets the split search stream instead of gather; see kernels.partition."
+                             "frac_traffic for the fraction of peak on the bytes it really moves",
+                "l2_scan_search": "algorithmic bytes = SURVEY 8d's 12 B per (row, feature); the streaming kernel reads 8 B "
+                                  "(frac_traffic)",
+                "sort_radix_pass": "4-byte keys + 4-byte row ids, 4 passes of 8-bit digits",
             }
             if dom in notes:
                 roofline["note"] = notes[dom]
         cpu = None
         if world == 1 and not args.no_cpu:
-            rows = args.cpu_rows
+            rows = reference_rows(args, 6)      # about 20 s of CPU work
             secs = cpu_fit_seconds(rows, F, D)
             cpu = {"value": rows * F / secs, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{rows} x {F} row sample of the same recipe, whole depth-{D} fit, "
@@ -315,6 +354,7 @@ def run_b200(args):
                        "rows": N, "features": F, "max_depth": D, "nodes": tree.max_node_ + 1,
                        "l2_flush": "inputs (X %.1f GB per GPU) exceed the 126 MB L2" % (X.numel() * 8 / 1e9)},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "inference": inference, "tree_sha": tree_sha,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(out))
@@ -322,13 +362,80 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch from the committed ncu capture of this kernel, if there is one."""
+def ncu_traffic(kernel, per_launch=False):
+    """dram bytes (read + write) of the launches of one kernel class in ONE step of the 1-GPU C4 fit, from the
+    committed ncu capture (profiles/ncu_traffic.json: {"class": {"bytes_per_step": .., "launches_per_step": ..}})."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p)).get(kernel)
+        rec = json.load(open(p)).get(kernel)
+        if not isinstance(rec, dict):
+            return None
+        return rec["bytes_per_step"] / rec["launches_per_step"] if per_launch else rec["bytes_per_step"]
     except Exception:
         return None
+
+
+def tree_digest(tree):
+    """SHA-256 over the five tree arrays up to max_node_ (leaf values included: they come out of the same
+    deterministic kernels on every rank count, so the digest must not depend on the number of GPUs...
+    except for the last bits of node sums, which a look-back scan may group differently from run to run;
+    values are therefore rounded to 12 significant digits before hashing)."""
+    import hashlib
+    n = tree.max_node_ + 1
+    t = tree.tree_
+    h = hashlib.sha256()
+    for name in ("children_left", "children_right", "feature", "threshold"):
+        h.update(np.ascontiguousarray(getattr(t, name)[:n]).tobytes())
+    v = np.asarray(t.value[:n], dtype=np.float64)
+    h.update(np.array([float("%.11e" % x) for x in v]).tobytes())
+    return h.hexdigest()
+
+
+def measure_inference(args, torch, dist, ctx, tree, world, rank, dev, barrier):
+    """utils.inference over args.inference_rows device-resident rows per GPU (weak scaling over rows)."""
+    from np_decision_tree_b200.decision_tree import utils
+    rows, F = args.inference_rows, args.features
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    while rows * F * 8 > 0.6 * free_b and rows > 1_000_000:
+        rows //= 2
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED * 7 + 1000 + rank)
+    Xq = torch.randn((rows, F), dtype=torch.float64, device=dev, generator=g)
+    torch.cuda.synchronize()
+    ctx.profile_enable(True)
+    for _ in range(3):
+        out = utils.inference(Xq, tree)
+    ctx.profile_reset()
+    barrier()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = utils.inference(Xq, tree)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    kern = ctx.profile().get("predict", {"ms": 0.0, "alg_bytes": 0.0, "launches": 0})
+    ctx.profile_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    peak, _ = measured_peak()
+    kern_ms = kern["ms"] / max(1, kern["launches"])
+    alg = kern["alg_bytes"] / max(1, kern["launches"])
+    res = {"rows_per_gpu": rows, "rows": rows * world, "features": F, "ms_per_call": ms,
+           "value": rows * world / (ms * 1e-3), "unit": "rows/s",
+           "rows_features_per_s": rows * world * F / (ms * 1e-3),
+           "kernel_ms": kern_ms, "alg_bytes_per_row": alg / rows if rows else None,
+           "achieved_gbs": alg / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None,
+           "frac": alg / (kern_ms * 1e-3) / 1e9 / peak if kern_ms > 0 else None,
+           "accounting": "32 B x mean path length + 8 B per row (SURVEY 8d), this rank's kernel; ms_per_call is the "
+                         "whole utils.inference call (tree upload + kernel), max over ranks",
+           "checksum": float(out.sum().item())}
+    del Xq, out
+    torch.cuda.empty_cache()
+    return res
 
 
 def bind_to_gpu_numa_node(dev_index):
@@ -363,35 +470,55 @@ def measure_e2e(args, torch, dist, one, fit_sharded, ctx, X, y, last, lo, hi, wo
     torch.cuda.synchronize()
     h2d = (N * Fl + N + (N if last is not None else 0)) * 8
     tree_bytes = (2 ** (D + 1) - 1) * 40
+    api = ("decision_tree.one.build_regression_tree(numpy X, numpy y)" if world == 1
+           else "sharded.fit_sharded(host X slice, host y)")
+    del X
+    torch.cuda.empty_cache()
+
+    def timed(step):
+        step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([max(e0.elapsed_time(e1) / args.e2e_steps * 1e-3, wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # (1) pinned host buffers
     if world == 1:
         Xn, yn = hX.numpy(), hy.numpy()
-
-        def step():
-            return one.build_regression_tree(Xn, yn, max_depth=D)   # the call a user of the reference makes
-        del X
+        pinned = timed(lambda: one.build_regression_tree(Xn, yn, max_depth=D))   # the call a user of the reference makes
     else:
-        def step():
-            # host tensors in: the library pipelines the H2D column batches with the sort
-            return fit_sharded(hX, hy, lo, F, last_col=hlast, max_depth=D, ctx=ctx)
-    torch.cuda.empty_cache()
-    step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.e2e_steps):
-        step()
-    e1.record()
-    barrier()
-    wall = (time.perf_counter() - t0) / args.e2e_steps
-    t = torch.tensor([max(e0.elapsed_time(e1) / args.e2e_steps * 1e-3, wall)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs = float(t.item())
-    return {"value": N * F / secs, "unit": UNIT, "ms_per_step": secs * 1e3, "steps": args.e2e_steps,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": tree_bytes,
-            "api": "decision_tree.one.build_regression_tree(numpy X, numpy y)" if world == 1
-                   else "sharded.fit_sharded(pinned host X slice, host y)",
+        # host tensors in: the library pipelines the H2D column batches with the sort
+        pinned = timed(lambda: fit_sharded(hX, hy, lo, F, last_col=hlast, max_depth=D, ctx=ctx))
+    # (2) ordinary pageable memory, what np.random / np.load hand a user of the reference
+    pageable = None
+    try:
+        pX = torch.empty((N, Fl), dtype=torch.float64)
+        pX.copy_(hX)
+        py = hy.clone()
+        plast = hlast.clone() if hlast is not None else None
+        if world == 1:
+            pXn, pyn = pX.numpy(), py.numpy()
+            pageable = timed(lambda: one.build_regression_tree(pXn, pyn, max_depth=D))
+        else:
+            pageable = timed(lambda: fit_sharded(pX, py, lo, F, last_col=plast, max_depth=D, ctx=ctx))
+    except MemoryError:
+        pass
+    return {"value": N * F / pinned, "unit": UNIT, "ms_per_step": pinned * 1e3, "steps": args.e2e_steps,
+            "pinned_ms_per_step": pinned * 1e3,
+            "pageable_ms_per_step": None if pageable is None else pageable * 1e3,
+            "pageable_value": None if pageable is None else N * F / pageable,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": tree_bytes, "api": api,
+            "note": "value = pinned host buffers (the contract's definition); pageable_* = the same call on an ordinary "
+                    "numpy array, staged through the library's pinned bounce buffers",
             "host_placement": placement}
 
 

@@ -75,8 +75,10 @@ __device__ __forceinline__ u32 quantise(double x, const ColRange r) {
 }
 
 // per column: min / max over the finite values, as order-preserving u64 keys (atomicMin/Max)
+// `sample` > 1: only every sample-th group of 32 rows is read (the range is then a sampled one, see col_range_kernel)
 __global__ void __launch_bounds__(256) col_minmax_kernel(const double *__restrict__ X, int64_t N, int64_t ldx,
-                                                         int fb, u64 *__restrict__ kmin, u64 *__restrict__ kmax) {
+                                                         int fb, u64 *__restrict__ kmin, u64 *__restrict__ kmax,
+                                                         int sample) {
     __shared__ u64 smin[256], smax[256];
     const int tid = threadIdx.x;
     const int cg = blockIdx.y;
@@ -84,10 +86,10 @@ __global__ void __launch_bounds__(256) col_minmax_kernel(const double *__restric
     const int tcol = tid & (PREP_COLS - 1), trow = tid >> 3;
     u64 lo = ~0ull, hi = 0ull;
     // four rows in flight per thread (one load per iteration left the memory system idle)
-    const int64_t step = (int64_t)gridDim.x * 32;
+    const int64_t step = (int64_t)gridDim.x * 32 * sample;
     if (tcol < ncols) {
         const double *base = X + cg * PREP_COLS + tcol;
-        for (int64_t r = (int64_t)blockIdx.x * 32 + trow; r < N; r += 4 * step) {
+        for (int64_t r = (int64_t)blockIdx.x * 32 * sample + trow; r < N; r += 4 * step) {
             double x[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) x[u] = (r + u * step < N) ? base[(r + u * step) * ldx] : CUDART_NAN;
@@ -122,15 +124,23 @@ __device__ __forceinline__ double key_to_double(u64 k) {
     return __longlong_as_double((long long)b);
 }
 
+// widen > 0: the min / max come from a row SAMPLE, so the range is stretched by `widen` of its span on both
+// sides.  Values beyond it clamp to the first / last slot (still monotone); they tie there and the fix-up
+// pass orders them by the full key, or sends the column to the 64-bit path if there are more than it repairs.
 __global__ void col_range_kernel(const u64 *__restrict__ kmin, const u64 *__restrict__ kmax, int fb,
-                                 ColRange *__restrict__ out) {
+                                 ColRange *__restrict__ out, double widen) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= fb) return;
     ColRange r;
     r.mn = 0.0;
     r.scale = 0.0;
     if (kmin[f] <= kmax[f]) {
-        const double mn = key_to_double(kmin[f]), mx = key_to_double(kmax[f]);
+        double mn = key_to_double(kmin[f]), mx = key_to_double(kmax[f]);
+        const double pad = widen * (mx - mn);
+        if (pad > 0.0 && pad < CUDART_INF) {
+            mn -= pad;
+            mx += pad;
+        }
         const double span = mx - mn;
         r.mn = mn;
         if (span > 0.0 && span < CUDART_INF) r.scale = 4294967294.0 / span;
@@ -563,11 +573,8 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
     u32 *ghist = hist, *gbase = hist + (size_t)Fb * 8 * 256;
     int *flags = (int *)(gbase + (size_t)Fb * 8 * 256);
 
-    static int use32 = -1;
-    if (use32 < 0) {
-        const char *e = getenv("B200DT_SORT64");
-        use32 = (e && e[0] == '1') ? 0 : 1;
-    }
+    const char *e64 = getenv("B200DT_SORT64");   // read per call, like every other switch
+    const bool use32 = !(e64 && e64[0] == '1');
     if (use32) {
         // ---- 32-bit path: radix sort of the 32-bit images into d_alt, fix-up into d_out ------------
         CK(cudaMemsetAsync(flags, 0, (size_t)F * 4, ctx->stream));
@@ -582,10 +589,17 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
             CK(cudaMemsetAsync(kmin, 0xff, (size_t)Fb * 8, ctx->stream));
             CK(cudaMemsetAsync(kmax, 0x00, (size_t)Fb * 8, ctx->stream));
             {
-                int64_t rb = std::min<int64_t>((N + 31) / 32, std::max<int64_t>(1, 6ll * ctx->sm_count / groups));
-                LaunchScope ls(ctx, KC_SORT_PREPARE, 8.0 * (double)N * fb, 2);
-                col_minmax_kernel<<<dim3((unsigned)rb, groups), 256, 0, ctx->stream>>>(dX + c0, N, ldx, fb, kmin, kmax);
-                col_range_kernel<<<(fb + 127) / 128, 128, 0, ctx->stream>>>(kmin, kmax, fb, ranges);
+                // big columns: quantise between the min / max of a 1/32 row sample, stretched by 25 % on both
+                // sides (a full pass over X just for the range cost 7 ms of the C4 fit); the result is the exact
+                // stable order either way (fix-up / 64-bit fall-back)
+                const int sample = N >= (1 << 20) ? 32 : 1;
+                const int64_t groups32 = (N + 32 * (int64_t)sample - 1) / (32 * (int64_t)sample);
+                int64_t rb = std::min<int64_t>(groups32, std::max<int64_t>(1, 6ll * ctx->sm_count / groups));
+                LaunchScope ls(ctx, KC_SORT_PREPARE, 8.0 * (double)N * fb / sample, 2);
+                col_minmax_kernel<<<dim3((unsigned)rb, groups), 256, 0, ctx->stream>>>(dX + c0, N, ldx, fb, kmin, kmax,
+                                                                                       sample);
+                col_range_kernel<<<(fb + 127) / 128, 128, 0, ctx->stream>>>(kmin, kmax, fb, ranges,
+                                                                             sample > 1 ? 0.25 : 0.0);
             }
             // 4 passes: keys0 -> keys1 -> keys0 -> keys1 -> keys0 (sorted images), rows end in d_alt
             CKR(run_radix_sort<u32>(ctx, dX + c0, N, fb, ldx, (u32 *)keys0, (u32 *)keys1, d_out + c0 * col_stride,

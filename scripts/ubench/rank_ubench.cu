@@ -22,9 +22,21 @@ __device__ __forceinline__ u32 ballot_match(u32 d) {
     return peers;
 }
 
+__device__ __forceinline__ u32 redux_match(u32 d, int lane) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const u32 v = __reduce_or_sync(0xffffffffu, ((d >> b) & 1u) << lane);
+        peers &= ((d >> b) & 1u) ? v : ~v;
+    }
+    return peers;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256, 3) rank_kernel(u32 *out, int iters, u32 seed) {
     __shared__ u32 hist[8][256];
+    __shared__ u32 tbl[8][256];
+    if (V == 5) { for (int i = threadIdx.x; i < 8 * 256; i += 256) (&tbl[0][0])[i] = 0; __syncthreads(); }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
     u32 acc = 0;
@@ -38,9 +50,22 @@ __global__ void __launch_bounds__(256, 3) rank_kernel(u32 *out, int iters, u32 s
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const u32 d = (key[i] >> ((it & 3) * 8)) & 255u;
-            rank[i] = (V == 2 || V == 4) ? ballot_match(d) : __match_any_sync(0xffffffffu, d);
+            if (V == 5) {
+                // peer mask through a warp-private table: OR the lane bit in, read the word back, leader clears it
+                atomicOr(&tbl[warp][d], 1u << lane);
+                __syncwarp();
+                const u32 peers = tbl[warp][d];
+                __syncwarp();
+                if ((peers & lt) == 0u) tbl[warp][d] = 0;
+                __syncwarp();
+                rank[i] = peers;
+            } else if (V == 6) {
+                rank[i] = redux_match(d, lane);
+            } else {
+                rank[i] = (V == 2 || V == 4) ? ballot_match(d) : __match_any_sync(0xffffffffu, d);
+            }
         }
-        if (V <= 2) {
+        if (V <= 2 || V == 5) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const u32 d = (key[i] >> ((it & 3) * 8)) & 255u;
@@ -78,7 +103,7 @@ void run(const char *name, u32 *out, int sms) {
         if (r && ms < best) best = ms;
     }
     const double keys = (double)grid * 256 * ITEMS * iters;
-    printf("%-52s %8.3f ms  %7.1f Gkeys/s  -> 2.56 G keys in %.2f ms\n", name, best, keys / best * 1e-6, 2.56e9 / (keys / best * 1e3));
+    printf("%-52s %8.3f ms  %7.1f Gkeys/s  -> 2.56 G keys in %.2f ms\n", name, best, keys / best * 1e-6, 2.56e9 / (keys / best));
 }
 
 int main() {
@@ -89,5 +114,7 @@ int main() {
     run<2>("V2 8 ballots + plain LDS/STS", out, p.multiProcessorCount);
     run<3>("V3 match.any only", out, p.multiProcessorCount);
     run<4>("V4 8 ballots only", out, p.multiProcessorCount);
+    run<5>("V5 atomicOr table match + plain LDS/STS count", out, p.multiProcessorCount);
+    run<6>("V6 8 REDUX.OR only", out, p.multiProcessorCount);
     return 0;
 }

@@ -56,6 +56,31 @@ def test_argsort_special_values(dt):
     assert np.array_equal(gpu_argsort(dt, X), np.argsort(X, axis=0, kind="stable"))
 
 
+def test_argsort_sampled_range_outliers(dt):
+    """>= 2^20 rows: the 32-bit image is quantised between a SAMPLED min / max (1 row group in 32).  Values the
+    sample never saw clamp to the end slots: a few are repaired by the fix-up, many send the column to the
+    64-bit path -- the result is the exact stable order either way."""
+    n = (1 << 20) + 4097
+    rs = np.random.RandomState(77)
+    X = rs.standard_normal((n, 4))
+    hidden = np.arange(n)[(np.arange(n) // 32) % 32 != 0]            # rows outside the sampled groups
+    X[hidden[rs.permutation(hidden.size)[:20]], 0] = rs.uniform(50, 60, size=20)       # 20 high outliers
+    X[hidden[rs.permutation(hidden.size)[:7]], 0] = -rs.uniform(50, 60, size=7)        # 7 low ones
+    X[hidden[rs.permutation(hidden.size)[:500]], 1] = rs.uniform(1e3, 1e6, size=500)   # too many to repair
+    X[hidden[:40], 2] = 1e300                                                          # 40 equal outliers
+    X[:, 3] = np.where((np.arange(n) // 32) % 32 == 0, 1.5, rs.standard_normal(n))     # constant SAMPLE
+    assert np.array_equal(gpu_argsort(dt, X), np.argsort(X, axis=0, kind="stable"))
+
+
+def test_argsort_forced_64bit_path(dt, monkeypatch):
+    monkeypatch.setenv("B200DT_SORT64", "1")      # read at every call
+    rs = np.random.RandomState(78)
+    X = np.round(rs.standard_normal((70001, 5)) * 4) / 8
+    X[::9, 2] = -0.0
+    X[::10, 3] = np.nan
+    assert np.array_equal(gpu_argsort(dt, X), np.argsort(X, axis=0, kind="stable"))
+
+
 def test_argsort_golden(dt, golden_configs, c2_data):
     X, _ = c2_data      # distinct values per column: equals the reference's default-kind argsort
     assert sha(gpu_argsort(dt, X)) == str(golden_configs["argsort_sha"])
