@@ -19,7 +19,8 @@ sharded over the ranks (strong scaling).
   inference : utils.inference of the depth-10 tree of the timed fit over 12 500 000 x F device-resident
           rows PER GPU (row-sharded, no exchange; at 8 GPUs this is BASELINE.json configs[4],
           100 M x 256), rows/s and the fraction of the HBM roofline on 32 B x path + 8 B per row.
-  tree_sha : SHA-256 over the five tree arrays up to max_node_ -- identical at every GPU count.
+  tree_sha : SHA-256 over children / feature / threshold up to max_node_ (bit-exact quantities) -- identical at
+          every GPU count; value_sha: the node values rounded to 9 significant digits.
   roofline : the kernel class with the largest share of the step; achieved = algorithmic
           bytes / summed CUDA-event time of its launches in the timed
           region; peak = MEASURED_PEAKS.json hbm_gbs.
@@ -283,7 +284,7 @@ def run_b200(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
     value = N * F / (ms_per_step * 1e-3)
-    tree_sha = tree_digest(tree)
+    tree_sha, value_sha = tree_digest(tree)
 
     # ---- inference of that tree, row-sharded, device-resident (BASELINE.json configs[4] at 8 GPUs) ----
     inference = None
@@ -354,7 +355,7 @@ def run_b200(args):
                        "rows": N, "features": F, "max_depth": D, "nodes": tree.max_node_ + 1,
                        "l2_flush": "inputs (X %.1f GB per GPU) exceed the 126 MB L2" % (X.numel() * 8 / 1e9)},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-            "inference": inference, "tree_sha": tree_sha,
+            "inference": inference, "tree_sha": tree_sha, "value_sha": value_sha,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(out))
@@ -376,10 +377,10 @@ def ncu_traffic(kernel, per_launch=False):
 
 
 def tree_digest(tree):
-    """SHA-256 over the five tree arrays up to max_node_ (leaf values included: they come out of the same
-    deterministic kernels on every rank count, so the digest must not depend on the number of GPUs...
-    except for the last bits of node sums, which a look-back scan may group differently from run to run;
-    values are therefore rounded to 12 significant digits before hashing)."""
+    """(structure digest, value digest).  The first is SHA-256 over children_left, children_right, feature and
+    threshold up to max_node_ -- bit-exact quantities that must not depend on the number of GPUs.  Node values are
+    sums that a look-back scan may group differently from run to run (last bits), so they are hashed separately,
+    rounded to 9 significant digits (the north-star tolerance is 1e-9)."""
     import hashlib
     n = tree.max_node_ + 1
     t = tree.tree_
@@ -387,8 +388,8 @@ def tree_digest(tree):
     for name in ("children_left", "children_right", "feature", "threshold"):
         h.update(np.ascontiguousarray(getattr(t, name)[:n]).tobytes())
     v = np.asarray(t.value[:n], dtype=np.float64)
-    h.update(np.array([float("%.11e" % x) for x in v]).tobytes())
-    return h.hexdigest()
+    hv = hashlib.sha256(np.array([float("%.8e" % x) for x in v]).tobytes())
+    return h.hexdigest(), hv.hexdigest()
 
 
 def measure_inference(args, torch, dist, ctx, tree, world, rank, dev, barrier):

@@ -87,7 +87,7 @@ struct Session {
 };
 
 
-enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1, PIN_CLASS, PIN_WALK };
+enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1, PIN_CLASS, PIN_WALK, PIN_BOUNCE };
 
 void class_session_free(b200dt_ctx *ctx);  // classes.cu
 void row_session_free(b200dt_ctx *ctx);    // rows.cu
