@@ -70,6 +70,16 @@ int b200dt_l2_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int6
                          const double *X, int64_t ldx, const double *y, int64_t N, int variant,
                          int64_t *out_k, int64_t *out_f, double *out_gain, double *out_threshold);
 
+/* replaces: one.best_variance_improvements(ys) / _v0 / _v2 as stand-alone functions   ref one.py:56-63,66-78,81-93
+ * cumsums: (n, F) float64 row-major HOST array of column-wise running sums (np.cumsum(y[orders], axis=0)).
+ * variant 1: row-wise argmax of |S - (k+1) mean| over the features, then argmax over the rows of
+ *            np_gene(n) * value^2 -> (row, feature, gain)                                  (one.py:56-63)
+ * variant 0: flat row-major argmax of square(ratio_a * S - mean * ratio_b), float32 ratios  (one.py:66-78)
+ * variant 2: flat argmax of |ratio_a * S - mean * ratio_b|, returns the SQUARE of the best  (one.py:81-93)
+ * The arithmetic replays the reference's operation order with correctly rounded IEEE operations. */
+int b200dt_l2_score_cumsums(b200dt_ctx *ctx, const double *cumsums, int64_t n, int64_t F, int variant,
+                            int64_t *out_k, int64_t *out_f, double *out_score);
+
 /* ---- K3: L1 split search of ONE node, and the running median ------------------
  * replaces: greedy_regression_split[_v2](orders, X, y)   ref strategy_l1.py:125-140
  *           best_l1_improvements[_v2]                     ref strategy_l1.py:49-122
@@ -255,7 +265,10 @@ int b200dt_rows_threshold_counts(b200dt_ctx *ctx, int buffer, int64_t start, int
 /* regression with random thresholds (strategy.random_split_v2, ref strategy.py:136-146): register the float64
  * targets once, then per node: sum of y and row count left of every threshold (masks.T.dot(y), masks.sum(0)) and
  * out_node = {sum, min, max} of y over the node (np.mean for the leaf, np.unique(y).size <= 1 for base.py:16).
- * Floating-point sums, accumulated in no fixed order (the reference's go through BLAS). */
+ * Floating-point sums in a FIXED order that depends on the node's rows only (per-thread shares, then the row groups
+ * of a block in shared memory, then the blocks' slots): the sums are column-independent, so two columns whose
+ * thresholds cut off the SAME rows get bit-identical sums and tie exactly, as they do in the reference (whose sums
+ * go through BLAS, so their last bits are not defined by the reference itself). */
 int b200dt_rows_set_targets(b200dt_ctx *ctx, const double *y, int space);
 int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, const int32_t *cols,
                                int n_cols, const double *thresholds, double *out_sums,

@@ -21,7 +21,8 @@ __version__ = "0.1.0"
 def install_aliases():
     """Register this package's mirrors under the reference's module names."""
     from . import decision_tree as dt
-    from .decision_tree import one, strategy_l1, utils, np_stream_median, four, base, strategy, tree_builder
+    from .decision_tree import (one, strategy_l1, utils, np_stream_median, four, base, strategy, tree_builder,
+                                stream_median)
     sys.modules["decision_tree"] = dt
     sys.modules["decision_tree.one"] = one
     sys.modules["decision_tree.strategy_l1"] = strategy_l1
@@ -30,4 +31,5 @@ def install_aliases():
     sys.modules["decision_tree.base"] = base
     sys.modules["decision_tree.strategy"] = strategy
     sys.modules["decision_tree.tree_builder"] = tree_builder
+    sys.modules["decision_tree.stream_median"] = stream_median
     sys.modules["np_stream_median"] = np_stream_median   # ref strategy_l1.py:4 imports it top-level

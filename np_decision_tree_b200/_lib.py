@@ -45,6 +45,8 @@ _SIGNATURES = {
     "b200dt_l2_split_node": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_int,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                      ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
+    "b200dt_l2_score_cumsums": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                        ctypes.POINTER(c_dbl)]),
     "b200dt_l1_split_node": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                      ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),

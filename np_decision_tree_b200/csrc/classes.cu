@@ -805,7 +805,7 @@ static int class_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, 
     while ((1ll << row_bits) < N) ++row_bits;
     if ((int64_t)C > (1ll << (32 - row_bits)))
         return ctx->fail_msg("fit_classes: n_classes * N does not fit the packed 32-bit (class, row) entries");
-    class_session_free(ctx);
+    end_all_sessions(ctx);
     ClassSession *s = new (std::nothrow) ClassSession();
     if (!s) return ctx->fail_msg("fit_classes: out of host memory");
     ctx->class_session = s;

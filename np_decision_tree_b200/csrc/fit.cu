@@ -252,6 +252,7 @@ static void session_free(b200dt_ctx *ctx) {
     delete ctx->session;
     ctx->session = nullptr;
 }
+void tree_session_free(b200dt_ctx *ctx) { session_free(ctx); }
 
 static int make_child(Session *s, int parent, int is_left, int start, int n, double total) {
     HNode c;
@@ -279,7 +280,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     if (F_local > 65534) return ctx->fail_msg("fit: at most 65534 columns per GPU (shard the columns over more ranks)");
     if (max_depth < 0 || max_depth > 30) return ctx->fail_msg("fit: max_depth out of range [0, 30]");
     if (criterion != B200DT_L2 && criterion != B200DT_L1) return ctx->fail_msg("fit: unknown criterion");
-    session_free(ctx);
+    end_all_sessions(ctx);
     Session *s = new (std::nothrow) Session();
     if (!s) return ctx->fail_msg("fit: out of host memory");
     ctx->session = s;
@@ -1283,7 +1284,7 @@ int b200dt_argsort_columns(b200dt_ctx *ctx, const double *X, int64_t N, int64_t 
 static int stage_single_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const double *X,
                              int64_t ldx, const double *y, int64_t N, int criterion, int variant) {
     if (n <= 0 || F <= 0 || N <= 0) return ctx->fail_msg("split_node: empty input");
-    session_free(ctx);
+    end_all_sessions(ctx);
     Session *s = new (std::nothrow) Session();
     if (!s) return ctx->fail_msg("out of host memory");
     ctx->session = s;
@@ -1465,6 +1466,9 @@ int b200dt_predict(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64
     CK(cudaSetDevice(ctx->device));
     if (N <= 0) return 0;
     if (n_nodes <= 0 || n_nodes > (1ll << 30)) return ctx->fail_msg("predict: bad node count");
+    if (ctx->session || ctx->class_session || ctx->row_session)
+        return ctx->fail_msg("predict: a fit session is in progress on this context (they share its scratch buffers); "
+                             "finish it first or use another context");
     const double *dX = X;
     int64_t ld = ldx;
     if (x_space == B200DT_HOST) {

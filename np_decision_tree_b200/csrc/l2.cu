@@ -17,6 +17,7 @@
 //    reference's exact operation order and no FMA contraction, so bit-exact gain ties
 //    between features resolve exactly as in the reference (hard part 1).
 #include <algorithm>
+#include <vector>
 
 #include "l2_score.cuh"
 
@@ -474,6 +475,78 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
     }
 }
 
+// ---- stand-alone scoring of caller-supplied column cumsums (one.py:56-93 as plain functions) -------------
+// cums: (n, F) row-major.  One thread per sorted position k < n-1 replays the reference's arithmetic over the
+// F columns with correctly rounded, uncontracted operations; blocks reduce to one record each.
+//   variant 1: best_variance_improvements     (one.py:56-63): row-wise argmax of |S-(k+1)mean| over features (lowest
+//              feature on ties), then argmax over rows of np_gene * value^2 (lowest row on ties)
+//   variant 0: best_variance_improvements_v0  (one.py:66-78): flat row-major argmax of square(ra*S - mean*rb)
+//   variant 2: best_variance_improvements_v2  (one.py:81-93): flat argmax of |ra*S - mean*rb|, returns its square
+struct CumBest {
+    double score;
+    int k, f;
+};
+
+__global__ void __launch_bounds__(256) score_cumsums_kernel(const double *__restrict__ cums, int n, int F, int variant,
+                                                            CumBest *__restrict__ out) {
+    __shared__ CumBest sb[256];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    CumBest best;
+    best.score = -CUDART_INF;
+    best.k = 0x7fffffff;
+    best.f = 0x7fffffff;
+    if (k < n - 1) {
+        const double mean = __ddiv_rn(cums[(int64_t)(n - 1) * F + (F - 1)], (double)n);   // ys[-1][-1] / n
+        const double *row = cums + (int64_t)k * F;
+        if (variant == 1) {
+            const double resid = __dmul_rn((double)(k + 1), mean);                          // one.py:57
+            double v = -1.0;
+            int bf = 0;
+            for (int f = 0; f < F; ++f) {
+                const double t = fabs(__dsub_rn(row[f], resid));                             // one.py:58
+                if (t > v || (t != t && v == v)) {   // np.argmax: first maximum, NaN wins
+                    v = t;
+                    bf = f;
+                }
+            }
+            const double w = __ddiv_rn(1.0, __dmul_rn((double)__int2float_rn(k + 1), (double)(n - 1 - k)));
+            best.score = __dmul_rn(w, __dmul_rn(v, v));                                      // one.py:61
+            best.k = k;
+            best.f = bf;
+        } else {
+            const float lc = __int2float_rn(k + 1), rc = __int2float_rn(n - 1 - k);
+            const float ra = __fsqrt_rn(__frcp_rn(__fmul_rn(lc, rc)));
+            const float rb = __fsqrt_rn(__fdiv_rn(lc, rc));
+            const double mb = __dmul_rn(mean, (double)rb);
+            for (int f = 0; f < F; ++f) {
+                const double d = __dsub_rn(__dmul_rn((double)ra, row[f]), mb);
+                const double sc = variant == 0 ? __dmul_rn(d, d) : fabs(d);
+                if (sc > best.score || (sc != sc && best.score == best.score)) {
+                    best.score = sc;
+                    best.k = k;
+                    best.f = f;
+                }
+            }
+        }
+    }
+    sb[threadIdx.x] = best;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) {
+            const CumBest a = sb[threadIdx.x], b = sb[threadIdx.x + s];
+            // first maximum in row-major order; a NaN score wins over numbers like np.argmax
+            const bool a_nan = a.score != a.score, b_nan = b.score != b.score;
+            bool take_b;
+            if (a_nan != b_nan) take_b = b_nan;
+            else if (!a_nan && a.score != b.score) take_b = b.score > a.score;
+            else take_b = b.k < a.k || (b.k == a.k && b.f < a.f);
+            if (take_b) sb[threadIdx.x] = b;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sb[0];
+}
+
 }  // namespace
 
 static int persistent_grid(b200dt_ctx *ctx, const void *kernel, int threads, int64_t max_blocks) {
@@ -551,5 +624,41 @@ int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials
     else
         finalize_kernel<false><<<a.n_segs, 128, 0, ctx->stream>>>(a, partials, stage1, X, ldx, col_offset, out);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// replaces one.best_variance_improvements / _v0 / _v2 as stand-alone functions   (ref one.py:56-93)
+extern "C" int b200dt_l2_score_cumsums(b200dt_ctx *ctx, const double *cumsums, int64_t n, int64_t F, int variant,
+                                       int64_t *out_k, int64_t *out_f, double *out_score) {
+    if (!ctx) return 1;
+    if (!cumsums || !out_k || !out_f || !out_score) return ctx->fail_msg("l2_score_cumsums: null argument");
+    if (n < 2 || F < 1) return ctx->fail_msg("l2_score_cumsums: attempt to get argmax of an empty sequence (n < 2)");
+    if (n >= (1ll << 31) || F >= (1ll << 31)) return ctx->fail_msg("l2_score_cumsums: shape out of range");
+    if (variant < 0 || variant > 2) return ctx->fail_msg("l2_score_cumsums: variant must be 0, 1 or 2");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->session || ctx->class_session || ctx->row_session)
+        return ctx->fail_msg("l2_score_cumsums: a fit session is in progress on this context");
+    double *d_c;
+    CumBest *d_out;
+    const int blocks = (int)((n - 1 + 255) / 256);
+    CKR(scratch_get(ctx, SB_X, (size_t)n * F * 8, (void **)&d_c));
+    CKR(scratch_get(ctx, SB_OUT, (size_t)blocks * sizeof(CumBest), (void **)&d_out));
+    CK(cudaMemcpyAsync(d_c, cumsums, (size_t)n * F * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, KC_L2_EXACT, 8.0 * (double)n * F);
+        score_cumsums_kernel<<<blocks, 256, 0, ctx->stream>>>(d_c, (int)n, (int)F, variant, d_out);
+    }
+    CK(cudaGetLastError());
+    std::vector<CumBest> h(blocks);
+    CK(cudaMemcpyAsync(h.data(), d_out, (size_t)blocks * sizeof(CumBest), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CumBest best = h[0];
+    for (int b = 1; b < blocks; ++b) {   // blocks are in row order: a strictly greater score (or the first NaN) wins
+        const bool a_nan = best.score != best.score, b_nan = h[b].score != h[b].score;
+        if ((b_nan && !a_nan) || (!a_nan && !b_nan && h[b].score > best.score)) best = h[b];
+    }
+    *out_k = best.k;
+    *out_f = best.f;
+    *out_score = variant == 2 ? best.score * best.score : best.score;   // one.py:93 returns the square
     return 0;
 }

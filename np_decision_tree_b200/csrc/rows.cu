@@ -383,7 +383,7 @@ int b200dt_rows_begin(b200dt_ctx *ctx, const double *X, const int32_t *labels, i
     if (N >= (1ll << 31)) return ctx->fail_msg("rows_begin: N must be < 2^31");
     if (n_classes < 1 || n_classes > 4096) return ctx->fail_msg("rows_begin: n_classes must be in [1, 4096]");
     CK(cudaSetDevice(ctx->device));
-    row_session_free(ctx);
+    end_all_sessions(ctx);
     RowSession *s = new (std::nothrow) RowSession();
     if (!s) return ctx->fail_msg("rows_begin: out of host memory");
     ctx->row_session = s;

@@ -91,3 +91,11 @@ enum PinSlot { PIN_SEARCH = 0, PIN_PLAN, PIN_RESULT, PIN_MISC, PIN_L1, PIN_CLASS
 
 void class_session_free(b200dt_ctx *ctx);  // classes.cu
 void row_session_free(b200dt_ctx *ctx);    // rows.cu
+void tree_session_free(b200dt_ctx *ctx);   // fit.cu
+// The three session kinds (and predict) share the context's scratch buffers, so at most ONE may be live:
+// beginning any kind ends whatever was in progress on the context.
+static inline void end_all_sessions(b200dt_ctx *ctx) {
+    tree_session_free(ctx);
+    class_session_free(ctx);
+    row_session_free(ctx);
+}

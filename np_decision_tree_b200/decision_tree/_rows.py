@@ -157,13 +157,15 @@ def grow_random_regression(tree, X, y, max_depth, max_feature, min_improvement, 
             stop = n <= 2 * min_sample_leaf or depth >= max_depth
             node = None
             if not stop:
-                cols = all_cols if all_cols.size <= max_feature else np.random.permutation(all_cols)[:max_feature]
-                # base.py:16: a node whose targets are all equal is a leaf -- known from the node's min / max,
-                # which the search returns; the reference tests it BEFORE drawing, so look first
+                # base.py:16: a node whose targets are all equal is a leaf -- known from the node's min / max.  The
+                # reference tests it BEFORE find_best_split draws the column permutation (tree_builder.py:70-78,
+                # 44-48), so look first: a pure node must not consume a draw of the global generator
                 _, _, node = sess.threshold_sums(buffer, start, n, first, np.array([np.inf]))
                 if node[1] == node[2]:
                     stop = True
                 else:
+                    cols = (all_cols if all_cols.size <= max_feature
+                            else np.random.permutation(all_cols)[:max_feature])
                     best, threshold, improvement, node, n_left_expected = random_regression_node_search(
                         sess, buffer, start, n, cols, surrogate, to_variance)
                     stop = improvement < min_improvement

@@ -60,6 +60,33 @@ def np_gene(n):
     return np.reciprocal(np.arange(1, n, dtype=np.float32) * np.arange(n - 1, 0, -1))
 
 
+def _score_cumsums(ys, variant):
+    ys = np.ascontiguousarray(ys, dtype=np.float64)
+    if ys.ndim != 2:
+        raise ValueError("cumsums must be (n, F)")
+    ctx = context_for()
+    k, f, score = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    ctx.check(ctx.lib.b200dt_l2_score_cumsums(ctx.handle, ys.ctypes.data, ys.shape[0], ys.shape[1], variant,
+                                              ctypes.byref(k), ctypes.byref(f), ctypes.byref(score)))
+    return k.value, f.value, score.value
+
+
+def best_variance_improvements(ys):
+    """(row, column, gain) of the best split of the column cumsums ``ys`` (n, F) (one.py:56-63): per row the
+    feature with the largest |S - (k+1) mean|, then the row with the largest weighted square."""
+    return _score_cumsums(ys, 1)
+
+
+def best_variance_improvements_v0(cumsums):
+    """one.py:66-78: float32 ratio weights, flat argmax of the SQUARED scores."""
+    return _score_cumsums(cumsums, 0)
+
+
+def best_variance_improvements_v2(cumsums):
+    """one.py:81-93: float32 ratio weights, flat argmax of the absolute scores; returns the square of the best."""
+    return _score_cumsums(cumsums, 2)
+
+
 def greedy_regression_split(orders, x, y, v):
     """Best split of one node (one.py:96-107) -> (threshold, column, gain, left_rows).
 
@@ -93,6 +120,13 @@ def split_orders(orders, index, n_samples):
     ctx.check(ctx.lib.b200dt_split_orders(ctx.handle, orders.ctypes.data, n, F, index.ctypes.data, n_left,
                                           int(n_samples), left.ctypes.data, right.ctypes.data))
     return left, right
+
+
+def split_orders_v2(orders, index, n_samples):
+    """one.py:121-129 (unused in the reference): the same partition through an argsort of the masks.  Its
+    default-kind argsort is not stable and its reshape assumes ``orders.shape[1] == n_samples``, so the reference's
+    own result is only defined through ``split_orders``; this delegates to it."""
+    return split_orders(orders, index, n_samples)
 
 
 leaf_from_data = np.mean   # one.py:132

@@ -12,7 +12,8 @@ from numpy's GLOBAL generator; the draw stays on the host (same ``np.random.unif
 run reproduces the reference), the column min / max and the class counts left of the thresholds come
 from the GPU (csrc/rows.cu).  ``random_split_v2`` (strategy.py:136-146) is the regression counterpart: the
 GPU returns the sum of y and the row count left of every threshold.  ``random_split`` (rank-based cuts through
-a per-node argsort, strategy.py:174-185) is not accelerated.
+a per-node argsort, strategy.py:175-185) and ``greedy_split`` (strategy.py:188-208) run their argsort on the GPU
+(K1) and keep the reference's numpy arithmetic for the small per-column reductions.
 """
 import ctypes
 
@@ -158,13 +159,64 @@ def random_split_v2(X, y, cal_improvements=None):
         sess.close()
 
 
-def _not_accelerated(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError(
-            f"{name} (rank-based random cuts) is not part of the accelerated path; random_split_v2, "
-            "random_classify / random_classify_p_at_k and the exhaustive searches are")
-    fn.__name__ = name
-    return fn
+def cal_variance_improvements(y, masks):
+    """strategy.py:108-117: variance reduction of every column's (rows x columns) boolean left mask."""
+    total_count = y.size
+    total_sum = y.sum()
+    left_sums = masks.T.dot(y)
+    left_counts = masks.sum(axis=0)
+    return ((np.square(left_sums) / left_counts + np.square(total_sum - left_sums) / (total_count - left_counts))
+            / total_count - np.square(np.mean(y)))
 
 
-random_split = _not_accelerated("random_split")
+def cal_gini_improvements(y, masks):
+    """strategy.py:120-132: the same for one-hot targets (gini)."""
+    total_count = y.shape[0]
+    totals = y.sum(axis=0)
+    left = masks.T.dot(y)
+    left_counts = masks.sum(axis=0)
+    return (np.square(left).sum(axis=1) / left_counts
+            + np.square(totals - left).sum(axis=1) / (total_count - left_counts)
+            - np.square(totals).sum() / total_count) / total_count
+
+
+def _argsort_columns(X):
+    """np.argsort(X, axis=0) on the GPU (K1, b200dt_argsort_columns): (n, F) int64, stable."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    if X.ndim != 2:
+        raise ValueError("X must be 2-D")
+    out = np.empty(X.shape, dtype=np.int64)
+    if X.size:
+        ctx = context_for()
+        ctx.check(ctx.lib.b200dt_argsort_columns(ctx.handle, X.ctypes.data, X.shape[0], X.shape[1], X.shape[1],
+                                                 _lib.HOST, out.ctypes.data, _lib.HOST))
+    return out
+
+
+def random_split(X, y, cal_improvements=cal_variance_improvements):
+    """strategy.py:175-185: one random cutting rank per column (``np.random.choice``, the same call as the
+    reference, so a seeded run reproduces it), columns compared by ``cal_improvements`` of the masks
+    ``argsort(X) <= rank`` exactly as the reference forms them; the threshold is the column's value at that rank.
+    The per-column argsort -- the O(n log n) part -- runs on the GPU."""
+    indexes = _argsort_columns(X)
+    cutting_rank = np.random.choice(X.shape[0] - 1, X.shape[1])
+    improvements = cal_improvements(y, indexes <= cutting_rank)
+    best_index = np.argmax(improvements)
+    data_row_index = indexes[cutting_rank[best_index], best_index]
+    return best_index, X[data_row_index, best_index], improvements[best_index], np.zeros(X.shape[1], dtype=bool)
+
+
+def greedy_split(X, y):
+    """strategy.py:188-208: exhaustive variance search of one node with the flat (row, column) argmax of
+    sum_left^2 / n_left + sum_right^2 / n_right (``one.build_regression_tree`` is the whole-tree GPU form of the
+    same search).  GPU argsort, then the reference's column cumsums."""
+    orders = _argsort_columns(X)
+    total_sum = y.sum()
+    total_count = X.shape[0]
+    left_sums = np.cumsum(y[orders], axis=0)[:-1]
+    left_counts = np.arange(1, total_count)[:, np.newaxis]
+    surrogate = np.square(left_sums) / left_counts + np.square(total_sum - left_sums) / (total_count - left_counts)
+    best_row, best_column = np.unravel_index(np.argmax(surrogate), surrogate.shape)
+    best_threshold = X[orders[best_row, best_column], best_column]
+    best_improvement = surrogate[best_row, best_column] / total_count - np.square(np.mean(y))
+    return best_column, best_threshold, best_improvement, np.zeros(X.shape[1], dtype=bool)

@@ -12,6 +12,31 @@ from .one import DecisionTree, Task, split_orders  # noqa: F401  (strategy_l1.py
 from .np_stream_median import cummedian  # noqa: F401  (strategy_l1.py:4)
 
 
+def running_median_v2(a):
+    """strategy_l1.py:11-13: the (lower, upper) running median of ``a`` -- one kernel call here."""
+    return cummedian(np.asarray(a, dtype=np.float64))
+
+
+def _leaves_from(tree, X, y, leaf_from_data):
+    """Leaf values by an arbitrary reducer (strategy_l1.py:154,184 call ``leaf_from_data(y[task.orders])`` on the
+    (n_node, F) gather): rows are routed to their leaves on the GPU (inference_leaf), the reducer sees each leaf's
+    targets replicated over the F columns.  Exact for reducers that do not depend on the order inside a column."""
+    from .utils import inference_leaf
+    Xh = X.cpu().numpy() if hasattr(X, "is_cuda") else np.asarray(X)
+    yh = y.cpu().numpy() if hasattr(y, "is_cuda") else np.asarray(y, dtype=np.float64)
+    leaf = np.asarray(inference_leaf(Xh, tree)).ravel()
+    if leaf.shape[0] != yh.shape[0]:            # root-only tree: the (1,) quirk of utils.py:37
+        leaf = np.zeros(yh.shape[0], dtype=np.int64)
+    order = np.argsort(leaf, kind="stable")
+    ids, starts = np.unique(leaf[order], return_index=True)
+    bounds = np.append(starts, leaf.shape[0])
+    F = Xh.shape[1]
+    for i, node in enumerate(ids):
+        rows = order[bounds[i]:bounds[i + 1]]
+        tree.tree_.value[node] = leaf_from_data(np.broadcast_to(yh[rows][:, None], (rows.shape[0], F)))
+    return tree
+
+
 def best_l1_improvements_v2(ys):
     """(row, column, children L1 cost) of the best split of ``ys`` (n, F) (strategy_l1.py:87-122).
     The cost is minimised; ties go to the lowest row, then the lowest column (flat argmin).
@@ -61,10 +86,11 @@ def build_regression_tree_v2(X, y, max_depth=2, max_feature=100, min_improvement
                              leaf_from_data=np.median):
     """Fit an L1 regression tree (strategy_l1.py:173-200).  A node becomes a leaf when its best
     children COST is below ``min_improvement`` (strategy_l1.py:188), as in the reference."""
-    if leaf_from_data is not np.median:
-        raise NotImplementedError("only leaf_from_data=np.median (the reference default) runs on the GPU")
     tree = DecisionTree(2 ** (max_depth + 1))
-    return fit_into(tree, X, y, _lib.L1, max_depth, min_improvement, min_sample_leaf, 1).final()
+    fit_into(tree, X, y, _lib.L1, max_depth, min_improvement, min_sample_leaf, 1)
+    if leaf_from_data is not np.median:     # np.median leaves come out of the fit itself (the y-sorted column)
+        _leaves_from(tree, X, y, leaf_from_data)
+    return tree.final()
 
 
 def build_regression_tree(X, y, max_depth=2, max_feature=100, min_improvement=1e-7, min_sample_leaf=1,

@@ -134,25 +134,30 @@ def test_shard_columns():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_classification_mirror_rejects_what_is_not_accelerated():
-    """Host-side argument checks of the tree_builder mirror run before any GPU work."""
+def test_classification_mirror_host_side_checks():
+    """Host-side argument checks and helpers of the tree_builder / strategy mirrors run before any GPU work."""
     import numpy as np
     import pytest
+    from np_decision_tree_b200 import _lib
     from np_decision_tree_b200.decision_tree import strategy, tree_builder
     X = np.random.RandomState(0).standard_normal((20, 5))
     y = np.arange(20) % 2
-    with pytest.raises(NotImplementedError, match="split_method"):
-        tree_builder.build_classification_tree(X, y, split_method=strategy.random_split)   # regression splitter
-    with pytest.raises(NotImplementedError, match="random cuts"):
-        strategy.random_split(X, y)                                        # rank-based cuts: not accelerated
-    with pytest.raises(NotImplementedError, match="random_split_v2"):
+    # every splitter of the reference is now routed somewhere; without a GPU the first kernel call fails loudly
+    with pytest.raises((_lib.B200Error, OSError)):
+        strategy.random_split(X, y.astype(float))
+    with pytest.raises((_lib.B200Error, OSError)):
         tree_builder.build_regression_tree(X, y.astype(float))             # reference default: random_split
+    # the mask-based improvement helpers are plain numpy, like the reference's (strategy.py:108-132)
+    masks = X <= np.median(X, axis=0)
+    yy = X[:, 0] * 2.0
+    want = (np.square(masks.T.dot(yy)) / masks.sum(0) + np.square(yy.sum() - masks.T.dot(yy)) / (20 - masks.sum(0))) / 20 \
+        - np.square(np.mean(yy))
+    assert np.allclose(strategy.cal_variance_improvements(yy, masks), want)
+    assert strategy.cal_gini_improvements(np.eye(2)[y], masks).shape == (5,)
     assert strategy.surrogate_to_variance(8.0, 4, 1.0) == 1.0
     ls = np.array([1.0, 3.0])
     assert np.array_equal(strategy.surrogate_variance_improvements(ls, np.array([1, 2]), 6.0, 3),
                           np.square(ls) / np.array([1, 2]) + np.square(6.0 - ls) / np.array([2, 1]))
-    with pytest.raises(NotImplementedError, match="max_feature"):
-        tree_builder.build_classification_tree(X, y, max_feature=3, split_method=strategy.greedy_classification)
     with pytest.raises(IndexError):
         tree_builder.build_classification_tree(X, y + 5, split_method=strategy.greedy_classification)
     with pytest.raises(ValueError, match="one-hot"):
