@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(256, 3) partition4_kernel(const int *__restric
         const int f = (int)(t % n_cols), ti = (int)(t / n_cols);
         const TileDesc td = tiles[ti];
         const Plan4 sg = plan[td.seg];
-        const int off = td.tin * PT_TILE;
-        const int cnt = min(PT_TILE, sg.n - off);
+        const int off = td.tin * P4_TILE;
+        const int cnt = min(P4_TILE, sg.n - off);
         const int64_t cbase = (int64_t)f * col_stride + sg.start;
         const int *col = in + cbase + off;
         int rows[PT_ITEMS];
@@ -366,7 +366,7 @@ int launch_mark_left_virtual(b200dt_ctx *ctx, const int *orders, int64_t col_str
     return 0;
 }
 
-// plan4: host array of n_plan records {start, n, n_l, n_ll, n_rl, 0}; tiles: PT_TILE tiles of those segments
+// plan4: host array of n_plan records {start, n, n_l, n_ll, n_rl, 0}; tiles: P4_TILE tiles of those segments
 int launch_partition4(b200dt_ctx *ctx, const int *orders_in, int *orders_out, const double *y_in, double *y_out,
                       int64_t col_stride, int F_store, const void *d_plan4, const TileDesc *tiles, int n_tiles,
                       int64_t n_elems, const u32 *mask_a, const u32 *mask_b, int64_t N, u32 *codes, u64 *status,

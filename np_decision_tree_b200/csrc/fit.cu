@@ -888,7 +888,7 @@ static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
             if (!needed) continue;
             const int si = (int)plan4.size();
             plan4.push_back(p4);
-            for (int t = 0; t < (pp.n + PT_TILE - 1) / PT_TILE; ++t) tiles4.push_back(TileDesc{si, t});
+            for (int t = 0; t < (pp.n + P4_TILE - 1) / P4_TILE; ++t) tiles4.push_back(TileDesc{si, t});
             elems += pp.n;
         }
         if (!plan4.empty()) {

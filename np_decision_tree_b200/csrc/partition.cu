@@ -29,13 +29,17 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 }
 
 
-// One warp owns one tile of PT_TILE positions of one (node, column).  Every lane sees every
-// ballot, so the running left-count of the tile lives in registers: no shared memory, no
-// block barrier.  Persistent grid, static tile-major order (see l2.cu).
+// One BLOCK owns one tile of PT_TILE = 8 x PT_WARP consecutive positions of one (node, column); warp w moves the
+// PT_WARP positions [w * PT_WARP, (w+1) * PT_WARP) of it.  Every lane sees every ballot, so a warp's left-count
+// lives in registers; the eight counts meet in shared memory and ONE decoupled look-back per block (warp 0)
+// supplies the left-count of the earlier tiles of the same (node, column).  With one look-back chain entry per
+// 4096 positions the number of in-flight entries per column stays small (resident blocks / columns) even when a
+// rank owns few columns (feature-sharded fits: F_local = 32 at 8 GPUs), where per-warp entries made every tile
+// poll ~140 predecessors.  Persistent grid, static tile-major order (see l2.cu).
 // RELABEL: this level also hands out the new, node-contiguous row ids (relabel.cu): the look-up reads the
 // row's new id instead of its side bit, the side is `new id < first id of the right child`, and the new id
 // is what gets written.
-template <int PAY, bool RELABEL, bool PREFETCH>
+template <int PAY, bool RELABEL>
 __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
                                                            const double *__restrict__ y_in, double *__restrict__ y_out,
                                                            const double *__restrict__ w_in, double *__restrict__ w_out,
@@ -43,33 +47,22 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                                                            const TileDesc *__restrict__ tiles, int n_tiles,
                                                            const u32 *__restrict__ mask, u64 *status, u32 epoch,
                                                            int n_cols, int row_mask, const int *__restrict__ newid) {
+    __shared__ int s_cnt[2][8];
+    __shared__ int s_excl[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
     const int64_t total_tiles = (int64_t)n_tiles * n_cols;
-    const int64_t stride_tiles = (int64_t)gridDim.x * 8;
-    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += stride_tiles) {
+    int par = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, par ^= 1) {
         const int f = (int)(t % n_cols), ti = (int)(t / n_cols);
         const TileDesc td = tiles[ti];
         const SegDev sg = segs[td.seg];
-        const int off = td.tin * PT_TILE;
-        const int cnt = min(PT_TILE, sg.n - off);
+        const int off = td.tin * PT_TILE + warp * PT_WARP;
+        const int cnt = max(0, min(PT_WARP, sg.n - off));     // 0: this warp's part lies beyond the node's end
         const int64_t cbase = (int64_t)f * col_stride + sg.start;
         const int *col = in + cbase + off;
-        if (PREFETCH && lane == 0 && t + stride_tiles < total_tiles) {
-            // this warp's NEXT tile: pull its row ids and payload into L2 while the current tile is processed
-            const int64_t tn = t + stride_tiles;
-            const int fn = (int)(tn % n_cols);
-            const TileDesc tdn = tiles[tn / n_cols];
-            const int nstart = segs[tdn.seg].start, nn = segs[tdn.seg].n;
-            const int offn = tdn.tin * PT_TILE;
-            const u32 cntn = (u32)min(PT_TILE, nn - offn);
-            const int64_t nb = (int64_t)fn * col_stride + nstart + offn;
-            prefetch_l2_bulk(in + nb, cntn * 4u);
-            if (PAY == 1 || PAY == 2) prefetch_l2_bulk(y_in + nb, cntn * 8u);
-            if (PAY == 2) prefetch_l2_bulk(w_in + nb, cntn * 8u);
-        }
         int rows[PT_ITEMS];
-        if (cnt == PT_TILE) {
+        if (cnt == PT_WARP) {
 #pragma unroll
             for (int i = 0; i < PT_ITEMS; ++i) rows[i] = ld_stream_i32(col + i * 32 + lane);
         } else {
@@ -92,42 +85,59 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
             }
             leftbits |= (is_left ? 1u : 0u) << i;
         }
-        // every lane sees every ballot, so the tile's left count is register arithmetic; the ballots
+        // every lane sees every ballot, so the warp's left count is register arithmetic; the ballots
         // are recomputed in the write loop instead of being kept (registers -> occupancy)
         int run = 0;
 #pragma unroll
         for (int i = 0; i < PT_ITEMS; ++i) run += __popc(__ballot_sync(FULL_MASK, (leftbits >> i) & 1u));
-        int lb_row = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, run, lane);
+        if (lane == 0) s_cnt[par][warp] = run;
+        __syncthreads();
+        if (warp == 0) {
+            int total = lane < 8 ? s_cnt[par][lane] : 0;
+#pragma unroll
+            for (int m = 4; m >= 1; m >>= 1) total += __shfl_xor_sync(FULL_MASK, total, m);
+            total = __shfl_sync(FULL_MASK, total, 0);
+            const int excl = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, total, lane);
+            if (lane == 0) s_excl[par] = excl;
+        }
+        __syncthreads();
+        int lb_row = s_excl[par];     // left rows of the node before this warp's first position
+#pragma unroll
+        for (int w = 0; w < 7; ++w) lb_row += w < warp ? s_cnt[par][w] : 0;
+        // (the slots of this parity are rewritten two tiles later, after every warp has passed the barriers of the
+        // next tile, i.e. after these reads)
         int *ocol = out + cbase;
         const double *ycol = (PAY == 1 || PAY == 2) ? y_in + cbase + off : nullptr;
         double *oy = (PAY == 1 || PAY == 2) ? y_out + cbase : nullptr;
         const double *wcol = PAY == 2 ? w_in + cbase + off : nullptr;
         double *ow = PAY == 2 ? w_out + cbase : nullptr;
+        if (cnt > 0) {
 #pragma unroll
-        for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
-            double yv[4], wv[4];
-            if (PAY == 1 || PAY == 2) {
+            for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
+                double yv[4], wv[4];
+                if (PAY == 1 || PAY == 2) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = (i0 + u) * 32 + lane;
+                        yv[u] = e < cnt ? __ldcs(ycol + e) : 0.0;
+                        if (PAY == 2) wv[u] = e < cnt ? __ldcs(wcol + e) : 0.0;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int e = (i0 + u) * 32 + lane;
-                    yv[u] = e < cnt ? __ldcs(ycol + e) : 0.0;
-                    if (PAY == 2) wv[u] = e < cnt ? __ldcs(wcol + e) : 0.0;
+                    const int i = i0 + u;
+                    const u32 b = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
+                    const int e = i * 32 + lane;
+                    if (e < cnt) {
+                        const int lb = lb_row + __popc(b & lt);  // left rows before this element
+                        const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
+                        // streaming stores: the children are read by the NEXT kernel; keep L1 for the side mask
+                        __stcs(ocol + dest, rows[i]);
+                        if (PAY == 1 || PAY == 2) __stcs(oy + dest, yv[u]);
+                        if (PAY == 2) __stcs(ow + dest, wv[u]);
+                    }
+                    lb_row += __popc(b);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u;
-                const u32 b = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
-                const int e = i * 32 + lane;
-                if (e < cnt) {
-                    const int lb = lb_row + __popc(b & lt);  // left rows before this element
-                    const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
-                    // streaming stores: the children are read by the NEXT kernel; keep L1 for the side mask
-                    __stcs(ocol + dest, rows[i]);
-                    if (PAY == 1 || PAY == 2) __stcs(oy + dest, yv[u]);
-                    if (PAY == 2) __stcs(ow + dest, wv[u]);
-                }
-                lb_row += __popc(b);
             }
         }
     }
@@ -190,16 +200,13 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
     const int64_t total = (int64_t)n_tiles * F_store;
     int per_sm = 0;
     if (newid && pay != 1 && pay != 2) return ctx->fail_msg("partition: row relabelling needs a payload session");
-    static const bool prefetch = !(getenv("B200DT_NO_PREFETCH") && getenv("B200DT_NO_PREFETCH")[0] == '1');
-    const void *kern = pay == 3 ? (const void *)partition_kernel<3, false, true>
-                       : pay == 2 ? (newid ? (const void *)partition_kernel<2, true, true> : (const void *)partition_kernel<2, false, true>)
-                       : pay == 1 ? (newid ? (const void *)partition_kernel<1, true, true>
-                                           : prefetch ? (const void *)partition_kernel<1, false, true>
-                                                      : (const void *)partition_kernel<1, false, false>)
-                                  : (const void *)partition_kernel<0, false, true>;
+    const void *kern = pay == 3 ? (const void *)partition_kernel<3, false>
+                       : pay == 2 ? (newid ? (const void *)partition_kernel<2, true> : (const void *)partition_kernel<2, false>)
+                       : pay == 1 ? (newid ? (const void *)partition_kernel<1, true> : (const void *)partition_kernel<1, false>)
+                                  : (const void *)partition_kernel<0, false>;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
-    if (grid > (total + 7) / 8) grid = (total + 7) / 8;
+    if (grid > total) grid = total;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
     const double *yi = (pay == 1 || pay == 2) ? y_in : nullptr, *wi = pay == 2 ? w_in : nullptr;
     double *yo = (pay == 1 || pay == 2) ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) relabel_bins_kernel(const int *__restrict
         const SegDev sg = segs[td.seg];
         const int off = td.tin * PT_TILE;
 #pragma unroll 4
-        for (int i = 0; i < PT_ITEMS; ++i) {
+        for (int i = 0; i < PT_TILE / 32; ++i) {
             const int e = off + i * 32 + lane;
             if (e < sg.n) {
                 const int row = col[sg.start + e];
