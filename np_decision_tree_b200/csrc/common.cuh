@@ -121,7 +121,7 @@ enum ScratchId {
     SB_KEYS0 = 0, SB_KEYS1, SB_SORT_HIST, SB_SORT_STATUS, SB_ORD_A, SB_ORD_B, SB_X, SB_Y, SB_MASK,
     SB_SEG, SB_TILES, SB_PARTIAL, SB_RESULT, SB_STATUS_F, SB_STATUS_VAL, SB_STATUS_P, SB_MISC,
     SB_TMP_I64, SB_TMP2, SB_TREE, SB_OUT, SB_LEAF, SB_L1_A, SB_L1_B, SB_L1_C, SB_L1_D, SB_L1_E,
-    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_MASK_A, SB_CODES, SB_PLAN4, SB_NEWID, SB_ROWMAP, SB_RL_BINS, SB_RL_COUNTS, SB_COUNT
+    SB_L1_F, SB_L1_G, SB_L1_H, SB_LASTCOL, SB_STATUS_VAL2, SB_YPAY0, SB_YPAY1, SB_PLAN, SB_SORT_RANGE, SB_W, SB_YW, SB_WPAY0, SB_WPAY1, SB_TW, SB_MASK_A, SB_CODES, SB_PLAN4, SB_NEWID, SB_ROWMAP, SB_RL_BINS, SB_RL_COUNTS, SB_NODE_BEST, SB_COUNT
 };
 
 static inline int scratch_get(b200dt_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false) {

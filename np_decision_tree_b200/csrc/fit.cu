@@ -557,6 +557,8 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     a.n_segs = n_live;
     a.wpay = s->wpay[s->cur];
     a.row_map = s->relabeled ? s->d_rowmap : nullptr;
+    CKR(scratch_get(ctx, SB_NODE_BEST, (size_t)n_live * 8 + 64, (void **)&a.node_best));
+    CK(cudaMemsetAsync(a.node_best, 0, (size_t)n_live * 8, ctx->stream));
     int64_t max_records = 0;
     for (const SegDev &sg : s->h_segs) max_records = std::max<int64_t>(max_records, (int64_t)sg.np * s->F_local);
     Partial *d_sliced;

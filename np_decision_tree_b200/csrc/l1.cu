@@ -757,6 +757,7 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
     a.segs = s->d_segs;
     a.n_segs = n_live;
     a.row_map = nullptr;
+    a.node_best = nullptr;
     CKR(launch_finalize(ctx, a, s->d_partials, F, nullptr, s->dX, s->ldx, s->col_offset, d_out));
     return 0;
 }

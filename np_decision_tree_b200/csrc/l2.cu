@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
         const int off = td.tin * ST_TILE;
         const int cnt = min(ST_TILE, sg.n - off);
         const double *yp = a.ypay + (int64_t)f * a.col_stride + sg.start + off;
+        // best gain any warp has found in this node so far (bits of a non-negative double; 0 at level start)
+        long long nb_seen = 0;
+        if (VARIANT == 1) nb_seen = (long long)ld_relaxed_u64((const u64 *)(a.node_best + td.seg));
         if (lane == 0 && t + stride_tiles < total_tiles) {
             // this warp's NEXT tile -> L2, so its loads below do not wait on DRAM
             const int64_t tn = t + stride_tiles;
@@ -224,20 +227,31 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
         double m1 = -CUDART_INF, m2 = -CUDART_INF, sbest = 0.0, dbest = 0.0;
         int kbest = 0x7fffffff;
         if (VARIANT == 1 && n <= (1 << 24)) {
+            // gain(k) = dev^2 / den, den = (k+1)(n-1-k) advanced exactly.  Almost no position can beat -- or come
+            // within the near-tie margin of -- the best gain the NODE has produced so far (`node_best`, a running
+            // maximum shared by all warps working on the node), so positions are first tested without the division:
+            //      dev^2 > 0.9999999 * bound * den
+            // and only the survivors (a vanishing fraction once the bound has risen) are scored in full.  The
+            // position of the node's maximum and everything within 1e-7 of it always survive, whatever the timing,
+            // so the winner, the tie rule and the near-tie flag (1e-9) do not depend on the bound.
             double km = (double)(k0 + 1) * mean;
             double den = (double)(k0 + 1) * (double)(n - 1 - k0);
             double dd = (double)(n - 2 * k0 - 3);
+            double gate = 0.9999999 * __longlong_as_double(nb_seen);
 #pragma unroll 4
             for (int j = 0; j < nvalid; ++j) {
                 S += mine[j];
                 const double dev = S - km;
-                const double g = dev * dev * rcp_fast1(den);
-                m2 = fmax(m2, fmin(m1, g));
-                if (g > m1) {
-                    m1 = g;
-                    sbest = S;
-                    dbest = dev;
-                    kbest = k0 + j;
+                if (dev * dev > gate * den) {
+                    const double g = dev * dev * rcp_fast1(den);
+                    m2 = fmax(m2, fmin(m1, g));
+                    if (g > m1) {
+                        m1 = g;
+                        sbest = S;
+                        dbest = dev;
+                        kbest = k0 + j;
+                        gate = fmax(gate, 0.9999999 * g);
+                    }
                 }
                 km += mean;
                 den += dd;
@@ -277,6 +291,9 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             out.ppos = -1;
             out.pad_ = 0;
             partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
+            // raise the node's bound (non-negative doubles order like their bit patterns; NaN never gets here)
+            if (VARIANT == 1 && best.g > __longlong_as_double(nb_seen))
+                atomicMax(a.node_best + td.seg, __double_as_longlong(best.g));
         }
     }
 }

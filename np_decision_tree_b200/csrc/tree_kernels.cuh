@@ -71,6 +71,7 @@ struct LevelArgs {
     const SegDev *segs;
     int n_segs;
     const int *row_map;     // non-null after the rows were relabelled (relabel.cu): row id -> ORIGINAL row
+    long long *node_best;   // per live node: bits of the best gain found so far (streaming search), zeroed per level
 };
 
 #ifdef __CUDACC__
