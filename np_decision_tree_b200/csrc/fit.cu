@@ -381,6 +381,8 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         // rows whose side bits stay L1-resident (1.5 M rows = 183 KB of mask); B200DT_RELABEL_ROWS overrides
         // (0 = off; small values make small test problems take the relabelled path)
         s->relabel_window = 1500000;
+        const char *sb = getenv("B200DT_SCAN_BULK");
+        s->scan_bulk = sb && sb[0] == '1';
         const char *w = getenv("B200DT_RELABEL_ROWS");
         if (w && w[0]) s->relabel_window = atoll(w);
     }
@@ -476,7 +478,10 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     const int scan_tile = s->dw ? WT_TILE : l2_scan_tile(s->ypay[0] != nullptr);
     for (int i = 0; i < n_live; ++i) {
         const HNode &nd = s->nodes[s->live[i]];
-        const int ntiles = (nd.n + scan_tile - 1) / scan_tile;
+        // the streaming search copies its tiles with 16-byte aligned bulk copies: a node that starts at an odd
+        // position has its tile grid shifted down by one element (l2.cu)
+        const int shift = (s->scan_bulk && s->ypay[0] != nullptr && !s->dw) ? (nd.start & 1) : 0;
+        const int ntiles = (nd.n + shift + scan_tile - 1) / scan_tile;
         SegDev sg;
         sg.total = nd.total;
         sg.total_w = nd.total_w;
@@ -582,7 +587,8 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     }
     ScanStatus st;
     CKR(scratch_get(ctx, SB_STATUS_F, n_status * 16, (void **)&st.slot, true));
-    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant));
+    CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant,
+                       s->scan_bulk));
     CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
                         s->d_partials, s->variant));
     CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out));

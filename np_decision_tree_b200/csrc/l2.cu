@@ -17,6 +17,7 @@
 //    reference's exact operation order and no FMA contraction, so bit-exact gain ties
 //    between features resolve exactly as in the reference (hard part 1).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "l2_score.cuh"
@@ -159,6 +160,33 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
     }
 }
 
+// warp arg-best of per-lane (best gain, position) pairs: (gain desc, position asc) decides the winner lane, whose
+// prefix sum / deviation are broadcast; the runner-up is the best of the lanes' runner-ups and of the losing lanes'
+// bests.  29 shuffles instead of the 55 of a full-record butterfly.
+__device__ __forceinline__ void warp_argbest(double m1, double m2, double &sbest, double &dbest, int kbest, double &wg,
+                                             int &wk, double &r2) {
+    wg = m1;
+    wk = kbest;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const double og = shfl_xor_d(wg, m);
+        const int ok = __shfl_xor_sync(FULL_MASK, wk, m);
+        if (og > wg || (og == wg && ok < wk)) {
+            wg = og;
+            wk = ok;
+        }
+    }
+    const bool winner = kbest == wk && wk != 0x7fffffff;
+    const int wl = __ffs(__ballot_sync(FULL_MASK, winner)) - 1;
+    r2 = winner ? m2 : fmax(m1, m2);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) r2 = fmax(r2, shfl_xor_d(r2, m));
+    if (wl >= 0) {
+        sbest = shfl_d(sbest, wl);
+        dbest = shfl_d(dbest, wl);
+    }
+}
+
 // Streaming variant (sessions that carry y as a payload next to the row ids): the tile is 1024
 // positions of ypay, staged once in shared memory and read twice by the lane that owns 32
 // consecutive positions -- first to sum them (tile aggregate -> look-back), then to rebuild the
@@ -206,9 +234,15 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             }
         }
         __syncwarp();
-        double tsum = 0.0;
-#pragma unroll 8
-        for (int j = 0; j < ST_ITEMS; ++j) tsum += mine[j];
+        double ts0 = 0.0, ts1 = 0.0, ts2 = 0.0, ts3 = 0.0;   // four independent chains (fp64 add latency)
+#pragma unroll
+        for (int j = 0; j < ST_ITEMS; j += 4) {
+            ts0 += mine[j];
+            ts1 += mine[j + 1];
+            ts2 += mine[j + 2];
+            ts3 += mine[j + 3];
+        }
+        const double tsum = (ts0 + ts1) + (ts2 + ts3);
         double incl = tsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -273,27 +307,205 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             }
         }
         __syncwarp();  // sy is overwritten by the next tile
-        Cand best;
-        best.g = m1;
-        best.g2 = m2;
-        best.s = sbest;
-        best.dev = dbest;
-        best.k = kbest;
-        cand_warp_reduce(best);
+        double wg, r2;
+        int wk;
+        warp_argbest(m1, m2, sbest, dbest, kbest, wg, wk, r2);
         if (lane == 0) {
             Partial out;
-            out.score = best.g;
-            out.aux = best.dev;
-            out.lsum = best.s;
-            out.score2 = best.g2;
-            out.k = best.k == 0x7fffffff ? -1 : best.k;
+            out.score = wg;
+            out.aux = dbest;
+            out.lsum = sbest;
+            out.score2 = r2;
+            out.k = wk == 0x7fffffff ? -1 : wk;
             out.f = f;
             out.ppos = -1;
             out.pad_ = 0;
             partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
             // raise the node's bound (non-negative doubles order like their bit patterns; NaN never gets here)
-            if (VARIANT == 1 && best.g > __longlong_as_double(nb_seen))
-                atomicMax(a.node_best + td.seg, __double_as_longlong(best.g));
+            if (VARIANT == 1 && wg > __longlong_as_double(nb_seen))
+                atomicMax(a.node_best + td.seg, __double_as_longlong(wg));
+        }
+    }
+}
+
+// The same search with the tile brought into shared memory by BULK ASYNCHRONOUS COPIES (TMA, cp.async.bulk + mbarrier),
+// double-buffered: while a warp works on tile i, the 8 KB of its tile i+1 are already in flight into its other buffer,
+// and the copy engine writes shared memory directly (no LDG + STS pair per element; the register-staged kernel keeps the
+// LSU pipe 65 % busy and stalls a quarter of its time on its loads, ncu r02).  Selected with B200DT_SCAN_BULK=1.
+// MEASURED (10 M x 256, profiles/README.md): correct, LSU 65 -> 28 %, but 6.4 ms per level against 5.1 ms: two 8.7 KB
+// buffers per warp leave 12 warps per SM, too few to cover the dependent fp64 prefix chain, and the per-lane copies
+// (needed for a conflict-free padded layout) are serialised through the uniform datapath (ELECT / R2UR loop, 32 x
+// UBLKCP per tile).  Kept as the measured alternative; the default is the register-staged kernel above.
+// Every lane issues ONE 256-byte copy: its own 32 positions go to its own row of the buffer.  Rows are 34 doubles
+// (272 B) apart: 16-byte aligned as the copy engine requires, and a quarter-warp's 128-bit reads of its rows hit 32
+// different banks (lane l covers banks 4l .. 4l+3).  Global sources must be 16-byte aligned too, so the tile grid of
+// a node whose first position is odd is shifted down by one element (`o`); that one foreign element is never read.
+constexpr int SB_ROW = ST_ITEMS + 2;              // doubles per lane row
+constexpr int SB_BUF = 32 * SB_ROW;               // doubles per buffer (8704 B)
+constexpr int SCAN_WARPS = 4;                     // warps per block: 4 x 2 x 8704 B = 68 KB, 3 blocks per SM
+constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * 2 * SB_BUF * sizeof(double) + SCAN_WARPS * 2 * sizeof(u64);
+
+template <int VARIANT>
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 3) l2_scan_bulk_kernel(LevelArgs a, const TileDesc *__restrict__ tiles,
+                                                                          int n_tiles, ScanStatus st, u32 epoch,
+                                                                          Partial *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wbuf = reinterpret_cast<double *>(scan_smem) + (size_t)warp * 2 * SB_BUF;
+    u64 *bars = reinterpret_cast<u64 *>(reinterpret_cast<double *>(scan_smem) + (size_t)SCAN_WARPS * 2 * SB_BUF) + warp * 2;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int64_t total_tiles = (int64_t)n_tiles * a.F_search;
+    const int64_t stride_tiles = (int64_t)gridDim.x * SCAN_WARPS;
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_WARPS + warp;
+
+    // start the copies of tile t into buffer b: lane l copies the valid part of its own 32 positions
+    auto issue = [&](int64_t t, int b) {
+        const int f = (int)(t % a.F_search);
+        const TileDesc td = tiles[t / a.F_search];
+        const int start = a.segs[td.seg].start, n = a.segs[td.seg].n;
+        const int o = start & 1;
+        const int q0 = td.tin * ST_TILE - o + lane * ST_ITEMS;          // node position of this lane's element 0
+        const int jhi = max(0, min(ST_ITEMS, n - q0));
+        const u32 bytes = (u32)((jhi * 8 + 15) & ~15);
+        const u32 total = __reduce_add_sync(FULL_MASK, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(&bars[b], total);
+        __syncwarp();
+        if (bytes)
+            bulk_g2s(wbuf + (size_t)b * SB_BUF + lane * SB_ROW, a.ypay + (int64_t)f * a.col_stride + start + q0, bytes,
+                     &bars[b]);
+    };
+
+    if (t0 < total_tiles) issue(t0, 0);
+    int it = 0;
+    for (int64_t t = t0; t < total_tiles; t += stride_tiles, ++it) {
+        const int b = it & 1;
+        if (t + stride_tiles < total_tiles) {
+            fence_proxy_async_smem();      // buffer b^1 was read (generic proxy) in the previous iteration
+            issue(t + stride_tiles, b ^ 1);
+        }
+        const int f = (int)(t % a.F_search), ti = (int)(t / a.F_search);
+        const TileDesc td = tiles[ti];
+        const SegDev sg = a.segs[td.seg];
+        const int n = sg.n;
+        const int o = sg.start & 1;
+        const int q0 = td.tin * ST_TILE - o + lane * ST_ITEMS;
+        const int jlo = max(0, -q0);                                  // 1 only for the shifted first element of a node
+        const int jhi = max(jlo, min(ST_ITEMS, n - q0));              // positions of the node: [jlo, jhi)
+        const int jsc = max(jlo, min(ST_ITEMS, n - 1 - q0));          // positions that can be split points: [jlo, jsc)
+        // warp-uniform: every lane owns 32 scoreable positions (all tiles but a node's first / last)
+        const bool full = td.tin * ST_TILE - o >= 0 && td.tin * ST_TILE - o + ST_TILE <= n - 1;
+        // best gain any warp has found in this node so far (bits of a non-negative double; 0 at level start)
+        long long nb_seen = 0;
+        if (VARIANT == 1) nb_seen = (long long)ld_relaxed_u64((const u64 *)(a.node_best + td.seg));
+        const double *mine = wbuf + (size_t)b * SB_BUF + lane * SB_ROW;
+        const double2 *mine2 = reinterpret_cast<const double2 *>(mine);
+        mbar_wait(&bars[b], (u32)(it >> 1) & 1u);
+
+        double tsum = 0.0;
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < ST_ITEMS / 2; ++i) {
+                const double2 v = mine2[i];
+                tsum += v.x;
+                tsum += v.y;
+            }
+        } else {
+            for (int j = jlo; j < jhi; ++j) tsum += mine[j];
+        }
+        double incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double x = shfl_up_d(incl, d);
+            if (lane >= d) incl += x;
+        }
+        const double tile_total = shfl_d(incl, 31);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        double S = excl + (incl - tsum);   // sum of everything before this lane's first position
+
+        const double mean = sg.total * rcp_fast1((double)n);
+        double m1 = -CUDART_INF, m2 = -CUDART_INF, sbest = 0.0, dbest = 0.0;
+        int kbest = 0x7fffffff;
+        if (VARIANT == 1 && n <= (1 << 24)) {
+            // gain(k) = dev^2 / den, den = (k+1)(n-1-k) advanced exactly.  Almost no position can beat -- or come
+            // within the near-tie margin of -- the best gain the NODE has produced so far (`node_best`, a running
+            // maximum shared by all warps working on the node), so positions are first tested without the division:
+            //      dev^2 > 0.9999999 * bound * den
+            // and only the survivors (a vanishing fraction once the bound has risen) are scored in full.  The
+            // position of the node's maximum and everything within 1e-7 of it always survive, whatever the timing,
+            // so the winner, the tie rule and the near-tie flag (1e-9) do not depend on the bound.
+            const int k0 = q0 + jlo;
+            double km = (double)(k0 + 1) * mean;
+            double den = (double)(k0 + 1) * (double)(n - 1 - k0);
+            double dd = (double)(n - 2 * k0 - 3);
+            double gate = 0.9999999 * __longlong_as_double(nb_seen);
+#define L2_SCORE_ONE(YV, KPOS)                                          \
+    {                                                                   \
+        S += (YV);                                                      \
+        const double dev = S - km;                                      \
+        if (dev * dev > gate * den) {                                   \
+            const double g = dev * dev * rcp_fast1(den);                \
+            m2 = fmax(m2, fmin(m1, g));                                 \
+            if (g > m1) {                                               \
+                m1 = g;                                                 \
+                sbest = S;                                              \
+                dbest = dev;                                            \
+                kbest = (KPOS);                                         \
+                gate = fmax(gate, 0.9999999 * g);                       \
+            }                                                           \
+        }                                                               \
+        km += mean;                                                     \
+        den += dd;                                                      \
+        dd -= 2.0;                                                      \
+    }
+            if (full) {
+#pragma unroll 4
+                for (int i = 0; i < ST_ITEMS / 2; ++i) {
+                    const double2 v = mine2[i];
+                    L2_SCORE_ONE(v.x, q0 + 2 * i)
+                    L2_SCORE_ONE(v.y, q0 + 2 * i + 1)
+                }
+            } else {
+                for (int j = jlo; j < jsc; ++j) L2_SCORE_ONE(mine[j], q0 + j)
+            }
+#undef L2_SCORE_ONE
+            dbest = fabs(dbest);
+        } else {
+            for (int j = jlo; j < jsc; ++j) {
+                S += mine[j];
+                double dev = 0.0;
+                const double g = score_fast(S, q0 + j, n, mean, VARIANT, dev);
+                m2 = fmax(m2, fmin(m1, g));
+                if (g > m1) {
+                    m1 = g;
+                    sbest = S;
+                    dbest = dev;
+                    kbest = q0 + j;
+                }
+            }
+        }
+        __syncwarp();  // every lane is done with buffer b: the next iteration refills it
+        double wg, r2;
+        int wk;
+        warp_argbest(m1, m2, sbest, dbest, kbest, wg, wk, r2);
+        if (lane == 0) {
+            Partial out;
+            out.score = wg;
+            out.aux = dbest;
+            out.lsum = sbest;
+            out.score2 = r2;
+            out.k = wk == 0x7fffffff ? -1 : wk;
+            out.f = f;
+            out.ppos = -1;
+            out.pad_ = 0;
+            partials[(int64_t)(sg.pbase + td.tin * sg.pstep + sg.pside) * a.F_search + f] = out;
+            // raise the node's bound (non-negative doubles order like their bit patterns; NaN never gets here)
+            if (VARIANT == 1 && wg > __longlong_as_double(nb_seen))
+                atomicMax(a.node_best + td.seg, __double_as_longlong(wg));
         }
     }
 }
@@ -576,27 +788,32 @@ static int persistent_grid(b200dt_ctx *ctx, const void *kernel, int threads, int
 }
 
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles, int64_t n_elems,
-                   ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant) {
+                   ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant, bool bulk) {
     (void)ticket;
     if (n_tiles <= 0) return 0;
     const int64_t total = (int64_t)n_tiles * a.F_search;
     LaunchScope ls(ctx, KC_L2_SCAN, 12.0 * (double)n_elems * a.F_search);
     if (a.ypay) {
         // streaming kernel: tiles of ST_TILE positions (the host builds the tile list accordingly)
-        const size_t smem = 8 * ST_PITCH * sizeof(double);
+        const size_t smem = bulk ? SCAN_SMEM : 8 * ST_PITCH * sizeof(double);
+        const int threads = bulk ? SCAN_WARPS * 32 : 256;
         // (per context = per device: a process may drive several GPUs)
         if (!(ctx->attr_mask & 4u)) {
-            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * ST_PITCH * sizeof(double))));
+            CK(cudaFuncSetAttribute(l2_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * ST_PITCH * sizeof(double))));
+            CK(cudaFuncSetAttribute(l2_scan_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
+            CK(cudaFuncSetAttribute(l2_scan_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
             ctx->attr_mask |= 4u;
         }
-        const void *kern = variant == 1 ? (const void *)l2_scan_stream_kernel<1> : (const void *)l2_scan_stream_kernel<2>;
+        const void *kern = bulk ? (variant == 1 ? (const void *)l2_scan_bulk_kernel<1> : (const void *)l2_scan_bulk_kernel<2>)
+                                : (variant == 1 ? (const void *)l2_scan_stream_kernel<1> : (const void *)l2_scan_stream_kernel<2>);
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        int64_t grid = std::min<int64_t>((int64_t)per_sm * ctx->sm_count, (total + 7) / 8);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int wpb = threads / 32;
+        int64_t grid = std::min<int64_t>((int64_t)per_sm * ctx->sm_count, (total + wpb - 1) / wpb);
         LevelArgs a_ = a;
         void *args[] = {&a_, &tiles, &n_tiles, &st, &epoch, &partials};
-        CK(launch_resident(kern, (unsigned)grid, 256, args, smem, ctx->stream));
+        CK(launch_resident(kern, (unsigned)grid, threads, args, smem, ctx->stream));
         return 0;
     }
     // every block must be resident at once (tiles wait on earlier tiles): grid <= occupancy limit

@@ -67,6 +67,7 @@ struct Session {
     bool exact_round_done = false;
     // row relabelling (relabel.cu): once per fit, at the first level whose children all fit an L1-resident
     // window of the side mask, the partition hands out node-contiguous row ids
+    bool scan_bulk = false;          // B200DT_SCAN_BULK=1: the TMA double-buffered split search (l2.cu), shifted tile grid
     int64_t relabel_window = 0;      // rows; 0 = never relabel
     bool plan_relabel = false;       // the plan just decided relabels
     bool relabeled = false;

@@ -269,7 +269,8 @@ int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, d
                           int F_store, int64_t N);
 
 int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, int n_tiles,
-                   int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant);
+                   int64_t n_elems, ScanStatus st, u32 epoch, u32 *ticket, Partial *partials, int variant,
+                   bool bulk = false);
 // tile size the search of this session uses (the streaming kernel takes larger tiles)
 static inline int l2_scan_tile(bool payload) { return payload ? ST_TILE : WT_TILE; }
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small,

@@ -303,3 +303,16 @@ def test_relabelled_rows_duplicate_columns_and_weights(monkeypatch):
         assert np.array_equal(getattr(got.tree_, name), getattr(want.tree_, name)), name
     # node sums come out of a look-back scan whose grouping depends on timing: last bits may differ
     np.testing.assert_allclose(got.tree_.value, want.tree_.value, rtol=RTOL)
+
+
+# ---- the TMA (cp.async.bulk + mbarrier) double-buffered split search, B200DT_SCAN_BULK=1 -------------------------
+@pytest.mark.parametrize("seed,n,F,depth,yr,v", [(31, 60001, 6, 9, None, 1), (32, 30000, 5, 10, 50.0, 1),
+                                                 (33, 40000, 4, 7, None, 2), (34, 5003, 3, 8, None, 1)])
+def test_bulk_copy_scan_builds_the_same_tree(monkeypatch, seed, n, F, depth, yr, v):
+    """Tiles copied by per-lane bulk asynchronous copies into padded rows, odd node starts shifted to 16-byte
+    alignment, partial first / last tiles: same tree as the oracle."""
+    from np_decision_tree_b200.decision_tree import one
+    monkeypatch.setenv("B200DT_SCAN_BULK", "1")
+    X, y = small_problem(seed, n, F, yr)
+    want = oracle.fit_l2(X, y, max_depth=depth, v=v, sort_kind="stable")
+    assert_same_tree(one.build_regression_tree(X, y, max_depth=depth, v=v), want, what=f"bulk scan seed {seed}")
