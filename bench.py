@@ -87,7 +87,7 @@ def gen_column_torch(N, c, device):
 
 
 def gen_problem_torch(N, F, lo, hi, device):
-    """Columns [lo, hi) of X, the replicated y, and the global last column."""
+    """Columns [lo, hi) of X and the replicated y."""
     import torch
     X = torch.empty((N, hi - lo), dtype=torch.float64, device=device)
     for c in range(lo, hi):
@@ -97,8 +97,7 @@ def gen_problem_torch(N, F, lo, hi, device):
     for c, w in zip(cols, coef):
         col = X[:, c - lo] if lo <= c < hi else gen_column_torch(N, int(c), device)
         y += w * col
-    last = None if hi == F else gen_column_torch(N, F - 1, device)
-    return X, y, last
+    return X, y, None      # (third slot: the global last column, which ranks no longer need a copy of)
 
 
 def gen_problem_numpy(N, F):

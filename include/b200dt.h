@@ -145,9 +145,12 @@ int b200dt_fit_ex(b200dt_ctx *ctx, const double *X, const double *y, const doubl
  *              winner with the reference's tie rule and the owner marks the left rows in
  *              the side mask (device, N/32 words, caller sum-all-reduces it)
  *   partition -> stable partition of every local column by the reduced mask.
- * last_col: the rank's own copy of global column F_global-1, (N,) float64 with stride
- * last_col_ld (the reference reads the node total in that column's order, one.py:57);
- * NULL when the rank owns that column. */
+ * Nodes searched in the reference's sequential fp64 order (small nodes, near ties) need the node total in the
+ * order of global column F_global-1 (one.py:57).  The rank that owns that column computes it and publishes it in
+ * its candidate record (exact == 2, f == F_global-1, left_sum = total; other ranks emit exact == 2, f == -1);
+ * `decide` then reports need_exact and the next search_exact round runs the search on every rank.  So a level may
+ * take up to three search_exact / gather / decide rounds; levels without such nodes take none.
+ * last_col / last_col_ld: accepted for compatibility, ignored (no rank keeps a shadow copy of that column). */
 typedef struct b200dt_candidate {
     double gain;      /* the score the search MAXIMISES: L2 v==1: variance gain (one.py:61);
                          L2 v!=1: the un-squared ratio score (its square is the gain, one.py:93);
@@ -158,7 +161,8 @@ typedef struct b200dt_candidate {
     double threshold; /* X[orders[k,f], f]                                             */
     int32_t k;        /* sorted position                                               */
     int32_t f;        /* GLOBAL feature index                                          */
-    int32_t exact;    /* 1: scores follow the reference's sequential fp64 order         */
+    int32_t exact;    /* 1: scores follow the reference's sequential fp64 order; 2: no candidate, left_sum
+                         carries the node total in the last global column's order (see below)  */
     int32_t pad;
 } b200dt_candidate;
 

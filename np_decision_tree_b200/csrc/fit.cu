@@ -294,15 +294,12 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     s->min_improvement = min_improvement;
     s->min_sample_leaf = min_sample_leaf;
     const bool owns_last = (col_offset + F_local == F_global);
-    if (!owns_last && last_col == nullptr && criterion == B200DT_L2)
-        return ctx->fail_msg("fit: a rank that does not own the last global column needs last_col");
+    // (last_col is accepted for compatibility and no longer used: see Session::sharded)
+    (void)last_col;
+    (void)last_col_ld;
+    s->sharded = F_local != F_global;
     int F_store = (int)F_local;
-    if (!owns_last && last_col) {
-        s->total_col = F_store;
-        F_store += 1;
-    } else {
-        s->total_col = (int)F_local - 1;
-    }
+    s->total_col = owns_last ? (int)F_local - 1 : -1;
     if (criterion == B200DT_L1) {
         s->ycol = F_store;
         F_store += 1;
@@ -413,20 +410,6 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
     } else {
         CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
     }
-    if (!owns_last && last_col) {
-        const double *dl = last_col;
-        int64_t ld = last_col_ld;
-        if (space == B200DT_HOST) {
-            double *buf;
-            CKR(scratch_get(ctx, SB_LASTCOL, (size_t)N * 8, (void **)&buf));
-            CK(cudaMemcpy2DAsync(buf, 8, last_col, (size_t)last_col_ld * 8, 8, (size_t)N, cudaMemcpyHostToDevice,
-                                 ctx->stream));
-            dl = buf;
-            ld = 1;
-        }
-        CKR(sort_columns_device(ctx, dl, N, 1, ld, s->ord[0] + (int64_t)s->total_col * s->col_stride,
-                                s->ord[1] + (int64_t)s->total_col * s->col_stride, s->col_stride, k0, k1, kcap));
-    }
     if (s->ycol >= 0) {
         CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,
                                 s->ord[1] + (int64_t)s->ycol * s->col_stride, s->col_stride));
@@ -460,6 +443,8 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
         s->live.push_back(0);
     }
     s->force_exact.assign(s->live.size(), 0);
+    s->known_total.assign(s->live.size(), 0.0);
+    s->has_total.assign(s->live.size(), 0);
     return 0;
 }
 
@@ -589,9 +574,44 @@ static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool ex
     CKR(scratch_get(ctx, SB_STATUS_F, n_status * 16, (void **)&st.slot, true));
     CKR(launch_l2_scan(ctx, a, d_tiles, (int)tiles.size(), tile_elems, st, ctx->epoch, ticket, s->d_partials, s->variant,
                        s->scan_bulk));
-    CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
-                        s->d_partials, s->variant));
+    if (!s->sharded) {
+        CKR(launch_l2_exact(ctx, a, d_list, (int)small.size(), small_elems, s->total_col, s->d_exact_total,
+                            s->d_partials, s->variant));
+        CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out));
+        return 0;
+    }
+    // feature-sharded: nodes whose total is known (it came back with the previous gather) are searched now; for the
+    // others this round only publishes the total -- the owner of the last global column computes it, every rank
+    // emits a marked record, and `decide` asks for another exact round
+    std::vector<int> known, unknown;
+    int64_t known_elems = 0, unknown_elems = 0;
+    for (int i : small) {
+        if (s->has_total[i]) {
+            known.push_back(i);
+            known_elems += s->nodes[s->live[i]].n;
+        } else {
+            unknown.push_back(i);
+            unknown_elems += s->nodes[s->live[i]].n;
+        }
+    }
+    int *d_known, *d_unknown;
+    CKR(scratch_get(ctx, SB_TMP_I64, (known.size() + unknown.size() + 2) * 4 + 128, (void **)&d_known));
+    d_unknown = d_known + known.size() + 1;
+    const size_t off_lists = seg_bytes + 64 + (tiles.size() + 1) * sizeof(TileDesc) + (small.size() + 1) * 4 + 64;
+    CKR(upload(ctx, PIN_SEARCH, off_lists, known.data(), known.size(), d_known));
+    CKR(upload(ctx, PIN_SEARCH, off_lists + (known.size() + 1) * 4, unknown.data(), unknown.size(), d_unknown));
+    if (!known.empty()) {
+        CKR(upload(ctx, PIN_SEARCH, off_lists + (known.size() + unknown.size() + 2) * 4 + 64, s->known_total.data(),
+                   (size_t)n_live, s->d_exact_total));
+        CKR(launch_l2_exact(ctx, a, d_known, (int)known.size(), known_elems, 0, s->d_exact_total, s->d_partials,
+                            s->variant, true));
+    }
+    CKR(launch_clear_partials(ctx, a, d_unknown, (int)unknown.size(), s->d_partials));
+    const bool owner = s->total_col >= 0;
+    if (owner && !unknown.empty())
+        CKR(launch_l2_exact_totals(ctx, a, d_unknown, (int)unknown.size(), unknown_elems, s->total_col, s->d_exact_total));
     CKR(launch_finalize(ctx, a, s->d_partials, max_records, d_sliced, s->dX, s->ldx, s->col_offset, d_out));
+    CKR(launch_emit_totals(ctx, d_unknown, (int)unknown.size(), s->d_exact_total, owner ? s->F_global - 1 : -1, d_out));
     return 0;
 }
 
@@ -620,7 +640,26 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<b200dt_candidate> win(n_live);
     bool any_flag = false;
+    // records marked exact == 2 carry a node total (feature-sharded fits), not a candidate: remember the total and
+    // have the node searched sequentially in the next exact round
+    std::vector<char> totals_only(n_live, 0);
+    for (int i = 0; i < n_live; ++i)
+        for (int r = 0; r < n_ranks; ++r) {
+            const b200dt_candidate &c = h[(size_t)r * n_live + i];
+            if (c.exact != 2) continue;
+            totals_only[i] = 1;
+            if (c.f == s->F_global - 1) {
+                s->known_total[i] = c.left_sum;
+                s->has_total[i] = 1;
+            }
+        }
     for (int i = 0; i < n_live; ++i) {
+        if (totals_only[i]) {
+            if (!s->has_total[i]) return ctx->fail_msg("fit: no rank supplied the total of a node (last global column)");
+            s->force_exact[i] = 1;
+            any_flag = true;
+            continue;
+        }
         b200dt_candidate best = h[i];
         double second = best.gain2;
         for (int r = 1; r < n_ranks; ++r) {
@@ -829,6 +868,8 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
     s->fused_slots = s->next_fused_slots;
     s->live.swap(next_live);
     s->force_exact.assign(s->live.size(), 0);
+    s->known_total.assign(s->live.size(), 0.0);
+    s->has_total.assign(s->live.size(), 0);
     s->depth += 1;
     return 0;
 }

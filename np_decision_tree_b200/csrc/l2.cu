@@ -825,16 +825,81 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
     return 0;
 }
 
+// node totals in the order of column `total_col` (one.py:57), for the listed nodes
+int launch_l2_exact_totals(b200dt_ctx *ctx, const LevelArgs &a, const int *list, int n_list, int64_t n_elems,
+                           int total_col, double *exact_total) {
+    if (n_list <= 0) return 0;
+    LaunchScope ls(ctx, KC_L2_EXACT, 12.0 * (double)n_elems);
+    exact_total_kernel<<<(n_list + 7) / 8, 256, 0, ctx->stream>>>(a, list, n_list, total_col, exact_total);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// totals_given: exact_total[] already holds the totals of the listed nodes (feature-sharded fits: they come from
+// the rank that owns the last global column)
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small, int64_t n_elems,
-                    int total_col, double *exact_total, Partial *partials, int variant) {
+                    int total_col, double *exact_total, Partial *partials, int variant, bool totals_given) {
     if (n_small <= 0) return 0;
-    {
-        LaunchScope ls(ctx, KC_L2_EXACT, 12.0 * (double)n_elems);
-        exact_total_kernel<<<(n_small + 7) / 8, 256, 0, ctx->stream>>>(a, small_list, n_small, total_col, exact_total);
-    }
+    if (!totals_given) CKR(launch_l2_exact_totals(ctx, a, small_list, n_small, n_elems, total_col, exact_total));
     const int64_t warps = (int64_t)n_small * a.F_search;
     LaunchScope ls(ctx, KC_L2_EXACT, 12.0 * (double)n_elems * a.F_search);
     l2_exact_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(a, small_list, n_small, exact_total, partials, variant);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// feature-sharded fits: the candidate records of nodes whose total is still to be exchanged carry the total
+// (owner of the last global column: f = that column) or nothing (other ranks: f = -1); exact = 2 marks them
+__global__ void emit_totals_kernel(const int *__restrict__ list, int n_list, const double *__restrict__ exact_total,
+                                   int owner_col, b200dt_candidate *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const int seg = list[i];
+    b200dt_candidate c;
+    c.gain = 0.0;
+    c.aux = 0.0;
+    c.left_sum = owner_col >= 0 ? exact_total[seg] : 0.0;
+    c.gain2 = 0.0;
+    c.threshold = 0.0;
+    c.k = -1;
+    c.f = owner_col;
+    c.exact = 2;
+    c.pad = 0;
+    out[seg] = c;
+}
+
+// nodes that are NOT searched in this round must not leave stale candidate slots for the finalize pass
+__global__ void clear_partials_kernel(const int *__restrict__ list, int n_list, const SegDev *__restrict__ segs, int F,
+                                      Partial *__restrict__ partials) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list * F) return;
+    const SegDev sg = segs[list[i / F]];
+    Partial b;
+    b.score = -CUDART_INF;
+    b.aux = 0.0;
+    b.lsum = 0.0;
+    b.score2 = -CUDART_INF;
+    b.k = -1;
+    b.f = i % F;
+    b.ppos = -1;
+    b.pad_ = 0;
+    partials[(int64_t)(sg.pbase + sg.pside) * F + (i % F)] = b;
+}
+
+int launch_clear_partials(b200dt_ctx *ctx, const LevelArgs &a, const int *list, int n_list, Partial *partials) {
+    if (n_list <= 0) return 0;
+    LaunchScope ls(ctx, KC_MISC, 0.0);
+    const int64_t n = (int64_t)n_list * a.F_search;
+    clear_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(list, n_list, a.segs, a.F_search, partials);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_emit_totals(b200dt_ctx *ctx, const int *list, int n_list, const double *exact_total, int owner_col,
+                       b200dt_candidate *out) {
+    if (n_list <= 0) return 0;
+    LaunchScope ls(ctx, KC_MISC, 0.0);
+    emit_totals_kernel<<<(n_list + 127) / 128, 128, 0, ctx->stream>>>(list, n_list, exact_total, owner_col, out);
     CK(cudaGetLastError());
     return 0;
 }

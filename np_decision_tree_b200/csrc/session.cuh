@@ -67,6 +67,12 @@ struct Session {
     bool exact_round_done = false;
     // row relabelling (relabel.cu): once per fit, at the first level whose children all fit an L1-resident
     // window of the side mask, the partition hands out node-contiguous row ids
+    // feature-sharded L2 fits: the node totals the sequential-order search needs (the reference sums a node in the
+    // order of the LAST global column, one.py:57) are computed by the rank that owns that column and travel inside
+    // the candidate records (exact == 2) -- no rank keeps a shadow copy of the column
+    bool sharded = false;
+    std::vector<double> known_total;   // per live node
+    std::vector<char> has_total;
     bool scan_bulk = false;          // B200DT_SCAN_BULK=1: the TMA double-buffered split search (l2.cu), shifted tile grid
     int64_t relabel_window = 0;      // rows; 0 = never relabel
     bool plan_relabel = false;       // the plan just decided relabels

@@ -274,7 +274,13 @@ int launch_l2_scan(b200dt_ctx *ctx, const LevelArgs &a, const TileDesc *tiles, i
 // tile size the search of this session uses (the streaming kernel takes larger tiles)
 static inline int l2_scan_tile(bool payload) { return payload ? ST_TILE : WT_TILE; }
 int launch_l2_exact(b200dt_ctx *ctx, const LevelArgs &a, const int *small_list, int n_small,
-                    int64_t n_elems, int total_col, double *exact_total, Partial *partials, int variant);
+                    int64_t n_elems, int total_col, double *exact_total, Partial *partials, int variant,
+                    bool totals_given = false);
+int launch_l2_exact_totals(b200dt_ctx *ctx, const LevelArgs &a, const int *list, int n_list, int64_t n_elems,
+                           int total_col, double *exact_total);
+int launch_clear_partials(b200dt_ctx *ctx, const LevelArgs &a, const int *list, int n_list, Partial *partials);
+int launch_emit_totals(b200dt_ctx *ctx, const int *list, int n_list, const double *exact_total, int owner_col,
+                       b200dt_candidate *out);
 constexpr int FIN_SLICES_HOST = 64;  // == FIN_SLICES in l2.cu
 int launch_finalize(b200dt_ctx *ctx, const LevelArgs &a, const Partial *partials, int64_t max_records,
                     Partial *sliced, const double *X, int64_t ldx, int col_offset, b200dt_candidate *out,

@@ -55,9 +55,9 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
     X_local: (N, F_local) float64 torch tensor, CUDA or (pinned) host -- this rank's columns
              [col_offset, col_offset + F_local) of the global (N, n_features) matrix.
     y:       (N,) float64 CUDA tensor, replicated.
-    last_col: (N,) float64 CUDA tensor = global column n_features-1, required on ranks that do
-             not own it (the reference takes the node total in that column's sorted order,
-             one.py:57; see include/b200dt.h).
+    last_col: accepted for compatibility and ignored (round 1 kept a shadow copy of the last global column on
+             every rank; the node totals the reference takes in that column's order, one.py:57, now travel
+             inside the candidate records of the rank that owns the column).
     Returns a DecisionTree identical on every rank.
     """
     import torch
@@ -100,15 +100,19 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
         gathered = gather_candidates(cand, world, group)
         ctx.check(lib.b200dt_session_decide(h, gathered.data_ptr(), world, mask.data_ptr(),
                                             ctypes.byref(need_part), ctypes.byref(need_exact)))
-        if need_exact.value:
-            # near-tie between two candidates of a parallel-scan search: redo those nodes in the
-            # reference's sequential fp64 order on every rank, then decide again
+        rounds = 0
+        while need_exact.value:
+            # some nodes must be searched in the reference's sequential fp64 order (small nodes, or a near-tie
+            # between two candidates of a parallel-scan search).  That search needs the node total in the order
+            # of the LAST global column (one.py:57): the rank owning that column publishes it in its candidate
+            # record first (one round), then every rank searches (next round), then the decision stands.
+            rounds += 1
+            if rounds > 4:
+                raise _lib.B200Error("exact re-search did not resolve a tie")
             ctx.check(lib.b200dt_session_search_exact(h, cand.data_ptr()))
             gathered = gather_candidates(cand, world, group)
             ctx.check(lib.b200dt_session_decide(h, gathered.data_ptr(), world, mask.data_ptr(),
                                                 ctypes.byref(need_part), ctypes.byref(need_exact)))
-            if need_exact.value:
-                raise _lib.B200Error("exact re-search did not resolve a tie")
         if need_part.value:
             reduce_side_mask(mask, world, group)
             ctx.check(lib.b200dt_session_partition(h, mask.data_ptr()))

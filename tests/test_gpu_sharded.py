@@ -37,9 +37,8 @@ def fit_emulated(X, y, world, max_depth, criterion=0, v=1):
         ctx.set_stream(stream)
         Xl = Xd[:, lo:hi].contiguous()
         slices.append(Xl)
-        lc = None if hi == F else last.data_ptr()
         ctx.check(ctx.lib.b200dt_session_begin(ctx.handle, Xl.data_ptr(), yd.data_ptr(), N, hi - lo, hi - lo,
-                                               _lib.DEVICE, criterion, max_depth, 1e-7, 1, v, lo, F, lc, 1))
+                                               _lib.DEVICE, criterion, max_depth, 1e-7, 1, v, lo, F, None, 0))
         ctxs.append(ctx)
         masks.append(torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev))
     n_live = ctypes.c_int64()
@@ -58,7 +57,10 @@ def fit_emulated(X, y, world, max_depth, criterion=0, v=1):
                                                     ctypes.byref(p), ctypes.byref(e)))
             flags.append((p.value, e.value))
         assert len(set(flags)) == 1, "ranks disagree"
-        if flags[0][1]:
+        rounds = 0
+        while flags[0][1]:      # totals round(s) and / or the sequential-order search (see sharded.fit_sharded)
+            rounds += 1
+            assert rounds <= 4
             for ctx, c in zip(ctxs, cands):
                 ctx.check(ctx.lib.b200dt_session_search_exact(ctx.handle, c.data_ptr()))
             gathered = torch.cat(cands)
@@ -68,7 +70,7 @@ def fit_emulated(X, y, world, max_depth, criterion=0, v=1):
                 ctx.check(ctx.lib.b200dt_session_decide(ctx.handle, gathered.data_ptr(), world, m.data_ptr(),
                                                         ctypes.byref(p), ctypes.byref(e)))
                 flags.append((p.value, e.value))
-            assert flags[0][1] == 0
+            assert len(set(flags)) == 1, "ranks disagree"
         if flags[0][0]:
             total = torch.stack(masks).sum(dim=0, dtype=torch.int32)   # == all_reduce(SUM)
             for ctx, m in zip(ctxs, masks):
