@@ -34,13 +34,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), checked=False):
+    """checked=True builds libb200tree_checked.so with -DB200DT_BOUNDS_CHECK: device-side index assertions in the
+    hot kernels (load it with B200DT_CHECKED=1)."""
+    lib = LIB.replace("libb200tree.so", "libb200tree_checked.so") if checked else LIB
+    if checked:
+        extra = tuple(extra) + ("-DB200DT_BOUNDS_CHECK",)
+    elif not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
     procs = []
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.path.join(HERE, "build_checked" if checked else "build")
     os.makedirs(obj_dir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
@@ -59,10 +64,10 @@ def build(force=False, verbose=False, extra=()):
             print(out)
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True,
-                extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else ()))
+                extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else (), checked="--checked" in sys.argv))

@@ -111,6 +111,20 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
+        path = LIB_PATH
+        if os.environ.get("B200DT_CHECKED") == "1":
+            # the bounds-checked build (`python -m np_decision_tree_b200._build --checked`): every hot kernel asserts
+            # its indices on the device and traps with a message; used where compute-sanitizer is not available
+            path = LIB_PATH.replace("libb200tree.so", "libb200tree_checked.so")
+            if not os.path.exists(path):
+                raise B200Error(f"{path} is missing: build it with `python -m np_decision_tree_b200._build --checked`")
+            lib = ctypes.CDLL(path)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+            return lib
         if not os.path.exists(LIB_PATH):
             if os.environ.get("B200DT_BUILD") == "1":
                 from . import _build

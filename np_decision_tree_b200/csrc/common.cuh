@@ -230,6 +230,23 @@ static inline cudaError_t launch_resident(const void *kernel, unsigned grid, uns
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// Device-side index assertions of the bounds-checked build (-DB200DT_BOUNDS_CHECK, libb200tree_checked.so): the
+// substitute for compute-sanitizer memcheck where that tool is not available.  A failing check prints and traps.
+#ifdef B200DT_BOUNDS_CHECK
+#define DCHECK(cond)                                                                         \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            printf("B200DT_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                       \
+            __trap();                                                                        \
+        }                                                                                    \
+    } while (0)
+#else
+#define DCHECK(cond) \
+    do {             \
+    } while (0)
+#endif
+
 #define FULL_MASK 0xffffffffu
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }

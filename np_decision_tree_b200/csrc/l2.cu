@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             out.lsum = sbest;
             out.score2 = r2;
             out.k = wk == 0x7fffffff ? -1 : wk;
+            DCHECK(out.k < sg.n - 1 && out.k >= -1);
             out.f = f;
             out.ppos = -1;
             out.pad_ = 0;
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 3) l2_scan_bulk_kernel(LevelA
             out.lsum = sbest;
             out.score2 = r2;
             out.k = wk == 0x7fffffff ? -1 : wk;
+            DCHECK(out.k < sg.n - 1 && out.k >= -1);
             out.f = f;
             out.ppos = -1;
             out.pad_ = 0;
@@ -697,7 +699,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(LevelArgs a, const Partia
         if (w.k >= 0 && X) {
             int row = sg.vstart >= 0 ? a.orders[(int64_t)w.f * a.col_stride + sg.vstart + w.ppos]
                                      : a.orders[(int64_t)w.f * a.col_stride + sg.start + w.k];
+            DCHECK(row >= 0);
             if (a.row_map) row = a.row_map[row];
+            DCHECK(row >= 0 && w.k < sg.n);
             c.threshold = X[(int64_t)row * ldx + w.f];  // one.py:104-105: a data value, not a midpoint
         }
         out[seg] = c;

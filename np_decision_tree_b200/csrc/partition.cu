@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
             const bool ok = PAY == 3 ? (i * 32 + lane < cnt) : (row >= 0);
             bool is_left;
             if (RELABEL) {
+                DCHECK(!ok || row >= 0);
                 const int nid = ok ? __ldg(newid + row) : 0x7fffffff;
+                DCHECK(!ok || (nid >= sg.start && nid < sg.start + sg.n));
                 is_left = nid < sg.start + sg.nleft;   // the left child takes the ids [start, start + nleft)
                 rows[i] = nid;
             } else {
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
                     if (e < cnt) {
                         const int lb = lb_row + __popc(b & lt);  // left rows before this element
                         const int dest = ((leftbits >> i) & 1u) ? lb : sg.nleft + (off + e - lb);
+                        DCHECK(dest >= 0 && dest < sg.n && lb <= sg.nleft && (((leftbits >> i) & 1u) ? lb < sg.nleft : true));
                         // streaming stores: the children are read by the NEXT kernel; keep L1 for the side mask
                         __stcs(ocol + dest, rows[i]);
                         if (PAY == 1 || PAY == 2) __stcs(oy + dest, yv[u]);

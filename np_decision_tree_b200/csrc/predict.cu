@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) predict_kernel(const double *__restrict__
             const bool go_left = __ldg(x + f) <= threshold[node];  // utils.py:22
             const int nxt = go_left ? l : r;                       // utils.py:23-24
             if (nxt == -1) break;                                  // utils.py:28-30: stay
+            DCHECK(nxt >= 0 && nxt < n_nodes && f >= 0 && f < (int)F);
             node = nxt;
         }
         if (out_value) out_value[row] = t.value[node];

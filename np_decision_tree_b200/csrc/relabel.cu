@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) relabel_assign_kernel(const unsigned shor
             if (b != RL_NONE) {
                 if ((peers & lt) == 0u) bins[b] = base + __popc(peers);
                 const int nid = base + __popc(peers & lt);
+                DCHECK(nid >= 0 && (int64_t)nid < N);
                 newid[r] = nid;
                 map_new[nid] = map_old ? map_old[r] : (int)r;
             }

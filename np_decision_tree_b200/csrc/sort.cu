@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const u32 pos = my_hist[RS_DIGIT(i)] + rank[i];
+            DCHECK(pos < (u32)RS_TILE);
             sm.keys[pos] = key[i];
             sm.vals[pos] = val[i];
         }
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
         if (full || pos < count) {
             const KeyT k = sm.keys[pos];
             const u32 dest = sm.gofs[(u32)(k >> shift) & 255u] + (u32)pos;
+            DCHECK((int64_t)dest < N);
             if (!LAST) kout[dest] = k;
             vout[dest] = sm.vals[pos];
         }
