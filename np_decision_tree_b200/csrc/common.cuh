@@ -381,4 +381,5 @@ struct Partial {
 // cross-file entry points (host side)
 int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
                         int *d_orders_out, int *d_orders_alt, int64_t col_stride, u64 *ext_keys0 = nullptr,
-                        u64 *ext_keys1 = nullptr, int64_t ext_key_capacity = 0);
+                        u64 *ext_keys1 = nullptr, int64_t ext_key_capacity = 0, const double *y = nullptr,
+                        double *ypay_out = nullptr);

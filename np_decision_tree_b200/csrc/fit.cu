@@ -400,15 +400,16 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
             const int64_t c0 = b * h2d_cols, fb = std::min<int64_t>(h2d_cols, F_local - c0);
             if (bounce) CKR(bounce_wait_batch(ctx, bounce.get(), b));   // the event must be RECORDED before the wait
             CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[b], 0));
+            // (y is on the device before the first batch: its payload comes out of the sort's fix-up pass)
             CKR(sort_columns_device(ctx, s->dX + c0, N, fb, s->ldx, s->ord[0] + c0 * s->col_stride,
-                                    s->ord[1] + c0 * s->col_stride, s->col_stride, k0, k1, kcap));
-            if (s->ypay[0])   // y is on the device before the first batch: gather its payload now
-                CKR(launch_gather_payload(ctx, s->ord[0] + c0 * s->col_stride, s->dy,
-                                          s->ypay[0] + c0 * s->col_stride, s->col_stride, (int)fb, N));
+                                    s->ord[1] + c0 * s->col_stride, s->col_stride, k0, k1, kcap, s->dy,
+                                    s->ypay[0] ? s->ypay[0] + c0 * s->col_stride : nullptr));
         }
         payload_cols_done = (int)F_local;
     } else {
-        CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap));
+        CKR(sort_columns_device(ctx, s->dX, N, F_local, s->ldx, s->ord[0], s->ord[1], s->col_stride, k0, k1, kcap,
+                                s->dy, s->ypay[0]));
+        if (s->ypay[0]) payload_cols_done = (int)F_local;
     }
     if (s->ycol >= 0) {
         CKR(sort_columns_device(ctx, s->dy, N, 1, 1, s->ord[0] + (int64_t)s->ycol * s->col_stride,

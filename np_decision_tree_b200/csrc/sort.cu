@@ -408,33 +408,53 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
 // start of each run insertion-sorts it (stable) by the full key.  A position is written by the tile
 // that owns the START of its run; runs longer than FIX_MAX_RUN flag the column (its output is then
 // discarded and the column re-sorted by the 64-bit path).
+// y / ypay (optional): the fit's y payload, ypay[f][j] = y[row at position j], leaves in the same pass (a separate
+// gather pass re-reads every row id).
+// Elements whose image is unique (~99 % for smooth data) are written as soon as their neighbours have been seen;
+// only the tied ones take the key gather / insertion sort / run-ownership path.
 __global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restrict__ X, int64_t ldx, int64_t N,
                                                          const u32 *__restrict__ q, int64_t qstride,
                                                          const int *__restrict__ in, int *__restrict__ out,
-                                                         int64_t col_stride, int *__restrict__ col_flags) {
+                                                         int64_t col_stride, int *__restrict__ col_flags,
+                                                         const double *__restrict__ y, double *__restrict__ ypay) {
     __shared__ u64 skey[FIX_TILE + FIX_MAX_RUN + 1];
     __shared__ u32 sq[FIX_TILE + FIX_MAX_RUN + 2];
     __shared__ int srow[FIX_TILE + FIX_MAX_RUN + 1];
+    __shared__ int any_tied;
     const int f = blockIdx.y;
     const int64_t a = (int64_t)blockIdx.x * FIX_TILE;   // first position this tile owns
     const int *col = in + (int64_t)f * col_stride;
     const u32 *qc = q + (int64_t)f * qstride;
     int *ocol = out + (int64_t)f * col_stride;
+    double *ycol = ypay ? ypay + (int64_t)f * col_stride : nullptr;
     // slot s <-> position a - 1 + s  (slot 0 = left neighbour, only used to recognise a run that
     // started in an earlier tile)
     const int nslots = (int)min((int64_t)(FIX_TILE + FIX_MAX_RUN + 1), N - a + 1);
     const int first = a == 0 ? 1 : 0;   // lowest slot holding a real element
-    for (int s = first + threadIdx.x; s < nslots; s += 256) {
-        srow[s] = col[a - 1 + s];
-        sq[s] = qc[a - 1 + s];
-    }
-    __syncthreads();
-    for (int s = first + threadIdx.x; s < nslots; s += 256) {
-        const bool tied = (s > first && sq[s - 1] == sq[s]) || (s + 1 < nslots && sq[s + 1] == sq[s]);
-        skey[s] = tied ? sortable_key(__ldg(X + (int64_t)srow[s] * ldx + f)) : 0ull;
-    }
-    __syncthreads();
     const int owned = (int)min((int64_t)FIX_TILE, N - a);
+    if (threadIdx.x == 0) any_tied = 0;
+    for (int s = first + threadIdx.x; s < nslots; s += 256) {
+        srow[s] = ld_stream_i32(col + a - 1 + s);
+        sq[s] = (u32)ld_stream_i32((const int *)qc + a - 1 + s);
+    }
+    __syncthreads();
+    bool mine_tied = false;
+    for (int s = first + threadIdx.x; s < nslots; s += 256) {
+        const u32 v = sq[s];
+        const bool tied = (s > first && sq[s - 1] == v) || (s + 1 < nslots && sq[s + 1] == v);
+        if (tied) {
+            skey[s] = sortable_key(__ldg(X + (int64_t)srow[s] * ldx + f));
+            mine_tied = true;
+        } else if (s >= 1 && s <= owned) {
+            // unique image: the element is in its final place
+            const int row = srow[s];
+            __stcs(ocol + a - 1 + s, row);
+            if (ycol) __stcs(ycol + a - 1 + s, __ldg(y + row));
+        }
+    }
+    if (mine_tied) any_tied = 1;
+    __syncthreads();
+    if (!any_tied) return;
     for (int s = 1 + threadIdx.x; s <= owned; s += 256) {
         const u32 v = sq[s];
         if (s > first && sq[s - 1] == v) continue;   // not the start of a run
@@ -463,13 +483,19 @@ __global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restric
     __syncthreads();
     for (int s = 1 + threadIdx.x; s < nslots; s += 256) {
         const u32 v = sq[s];
+        const bool tied = (s > first && sq[s - 1] == v) || (s + 1 < nslots && sq[s + 1] == v);
+        if (!tied) continue;
         int b = s, steps = 0;
         while (b > first && sq[b - 1] == v && steps <= FIX_MAX_RUN) {
             --b;
             ++steps;
         }
         // b == 0: the run began in an earlier tile; b > owned: it begins in the next one
-        if (steps <= FIX_MAX_RUN && b >= 1 && b <= owned) ocol[a - 1 + s] = srow[s];
+        if (steps <= FIX_MAX_RUN && b >= 1 && b <= owned) {
+            const int row = srow[s];
+            ocol[a - 1 + s] = row;
+            if (ycol) ycol[a - 1 + s] = __ldg(y + row);
+        }
     }
 }
 
@@ -541,9 +567,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
 // = row id of the j-th smallest value of column f.  d_alt is scratch of the same shape.
 // ext_keys0/1 (optional): caller-provided key double-buffer of ext_key_capacity uint64 each (the
 // fit lends its y-payload buffers, which are idle during the sort), instead of own scratch.
+int launch_gather_payload(b200dt_ctx *ctx, const int *orders, const double *y, double *ypay, int64_t col_stride,
+                          int F_store, int64_t N);
+
+// y / ypay_out (optional): also produce the y payload ypay_out[f][j] = y[d_out[f][j]] (fused into the fix-up pass).
 int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F, int64_t ldx,
                         int *d_out, int *d_alt, int64_t col_stride, u64 *ext_keys0, u64 *ext_keys1,
-                        int64_t ext_key_capacity) {
+                        int64_t ext_key_capacity, const double *y, double *ypay_out) {
     if (N <= 0 || F <= 0) return 0;
     if (N > (int64_t)RS_VAL_MASK) return ctx->fail_msg("argsort: N must be < 2^30");
     const int tiles = (int)((N + RS_TILE - 1) / RS_TILE);
@@ -606,10 +636,10 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
             // 4 passes: keys0 -> keys1 -> keys0 -> keys1 -> keys0 (sorted images), rows end in d_alt
             CKR(run_radix_sort<u32>(ctx, dX + c0, N, fb, ldx, (u32 *)keys0, (u32 *)keys1, d_out + c0 * col_stride,
                                     d_alt + c0 * col_stride, col_stride, ghist, gbase, status, tiles, ranges, true));
-            LaunchScope ls(ctx, KC_SORT_FIXUP, 12.0 * (double)N * fb);
+            LaunchScope ls(ctx, KC_SORT_FIXUP, (ypay_out ? 28.0 : 12.0) * (double)N * fb);
             sort_fixup_kernel<<<dim3((unsigned)((N + FIX_TILE - 1) / FIX_TILE), (unsigned)fb), 256, 0, ctx->stream>>>(
                 dX + c0, ldx, N, (const u32 *)keys0, N, d_alt + c0 * col_stride, d_out + c0 * col_stride, col_stride,
-                flags + c0);
+                flags + c0, y, ypay_out ? ypay_out + c0 * col_stride : nullptr);
         }
         CK(cudaGetLastError());
         // columns with a long run of equal 32-bit images take the 64-bit path
@@ -628,6 +658,9 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
             CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + (int64_t)c0 * col_stride,
                                     d_out + (int64_t)c0 * col_stride, col_stride, ghist, gbase, status, tiles, nullptr,
                                     false));
+            if (ypay_out)   // the fix-up's payload of a re-sorted column is stale
+                CKR(launch_gather_payload(ctx, d_out + (int64_t)c0 * col_stride, y, ypay_out + (int64_t)c0 * col_stride,
+                                          col_stride, fb, N));
             i = j + 1;
         }
         return 0;
@@ -638,5 +671,6 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
         CKR(run_radix_sort<u64>(ctx, dX + c0, N, fb, ldx, keys0, keys1, d_alt + c0 * col_stride,
                                 d_out + c0 * col_stride, col_stride, ghist, gbase, status, tiles, nullptr, false));
     }
+    if (ypay_out) CKR(launch_gather_payload(ctx, d_out, y, ypay_out, col_stride, (int)F, N));
     return 0;
 }
