@@ -273,16 +273,6 @@ __device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
     return v;
 }
 
-// Bulk-async prefetch of [p, p + bytes) into L2 (one instruction per tile instead of DRAM latency on the
-// critical path of the warp that streams it later).  The address is rounded down and the size up to 16 B;
-// the few extra bytes stay inside the buffer (callers keep >= 16 B of slack).
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, u32 bytes) {
-    const u64 a = (u64)p;
-    const u64 a0 = a & ~15ull;
-    const u32 n = (u32)((a - a0) + bytes + 15u) & ~15u;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
-}
-
 // ---- bulk asynchronous copies (TMA, 1-D) into shared memory, completion on an mbarrier ------------------------
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals) {

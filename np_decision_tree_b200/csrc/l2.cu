@@ -214,15 +214,6 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
         // best gain any warp has found in this node so far (bits of a non-negative double; 0 at level start)
         long long nb_seen = 0;
         if (VARIANT == 1) nb_seen = (long long)ld_relaxed_u64((const u64 *)(a.node_best + td.seg));
-        if (lane == 0 && t + stride_tiles < total_tiles) {
-            // this warp's NEXT tile -> L2, so its loads below do not wait on DRAM
-            const int64_t tn = t + stride_tiles;
-            const TileDesc tdn = tiles[tn / a.F_search];
-            const int nstart = a.segs[tdn.seg].start, nn = a.segs[tdn.seg].n;
-            const int offn = tdn.tin * ST_TILE;
-            prefetch_l2_bulk(a.ypay + (int64_t)(tn % a.F_search) * a.col_stride + nstart + offn,
-                             (u32)min(ST_TILE, nn - offn) * 8u);
-        }
         if (cnt == ST_TILE) {
 #pragma unroll
             for (int i = 0; i < ST_ITEMS; ++i) sy[i * 33 + lane] = __ldcs(yp + i * 32 + lane);

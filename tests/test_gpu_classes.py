@@ -45,6 +45,14 @@ def test_tree_matches_reference_golden(golden_classes, mods, name):
     assert np.array_equal(utils.inference(g[p + "X"], t), g[p + "pred"])
 
 
+@pytest.mark.parametrize("name", ["g0", "g2", "g5", "p1"])
+def test_three_pass_search_matches_reference_golden(golden_classes, mods, name, monkeypatch):
+    """B200DT_CLASS_3PASS=1: the histogram + scan + score kernels (the path > 32 classes and precision-at-1 with
+    many classes take anyway) forced for small class counts: same reference trees."""
+    monkeypatch.setenv("B200DT_CLASS_3PASS", "1")
+    test_tree_matches_reference_golden(golden_classes, mods, name)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_root_search_matches_reference_golden(golden_classes, mods, name):
     strategy, _, _ = mods
