@@ -277,6 +277,8 @@ int b200dt_rows_set_targets(b200dt_ctx *ctx, const double *y, int space);
 int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, const int32_t *cols,
                                int n_cols, const double *thresholds, double *out_sums,
                                int64_t *out_counts, double *out_node);
+/* n_left may be NULL: the split is then only queued (no host round trip); the caller already knows the count from
+ * threshold_counts / threshold_sums of the same (column, threshold). */
 int b200dt_rows_split(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, int32_t col,
                       double threshold, int64_t *n_left);
 int b200dt_rows_end(b200dt_ctx *ctx);

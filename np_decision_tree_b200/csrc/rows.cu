@@ -568,12 +568,11 @@ int b200dt_rows_threshold_sums(b200dt_ctx *ctx, int buffer, int64_t start, int64
 int b200dt_rows_split(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, int32_t col, double threshold,
                       int64_t *n_left) {
     if (!ctx) return 1;
-    if (!n_left) return ctx->fail_msg("rows_split: null argument");
     CK(cudaSetDevice(ctx->device));
     CKR(rows_check_segment(ctx, buffer, start, n));
     RowSession *s = ctx->row_session;
     if (col < 0 || col >= s->F) return ctx->fail_msg("rows_split: column id out of range");
-    *n_left = 0;
+    if (n_left) *n_left = 0;
     if (n == 0) return 0;
     const int n_blocks = (int)((n + SPLIT_BLOCK - 1) / SPLIT_BLOCK);
     int *d_blk;
@@ -590,6 +589,7 @@ int b200dt_rows_split(b200dt_ctx *ctx, int buffer, int64_t start, int64_t n, int
                                                                       out);
     }
     CK(cudaGetLastError());
+    if (!n_left) return 0;   // the caller knows the count (threshold_counts / threshold_sums): no host round trip
     long long h_total = 0;
     CK(cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

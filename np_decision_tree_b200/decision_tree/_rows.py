@@ -67,7 +67,13 @@ class RowSession:
                                                                counts.ctypes.data, node.ctypes.data))
         return sums, counts, node
 
-    def split(self, buffer, start, n, col, threshold):
+    def split(self, buffer, start, n, col, threshold, expected=None):
+        """Stable split of the node's row list.  With ``expected`` (the left count the search already produced) the
+        split is only queued: no host round trip per node."""
+        if expected is not None:
+            self.ctx.check(self.ctx.lib.b200dt_rows_split(self.ctx.handle, buffer, start, n, int(col), float(threshold),
+                                                          None))
+            return int(expected)
         n_left = ctypes.c_int64()
         self.ctx.check(self.ctx.lib.b200dt_rows_split(self.ctx.handle, buffer, start, n, int(col), float(threshold),
                                                       ctypes.byref(n_left)))
@@ -113,9 +119,7 @@ def grow_random(tree, X, labels, n_classes, max_depth, max_feature, min_improvem
                 tree.add_leaf(node_id, np.argmax(counts))
                 continue
             tree.add_binary_v2(node_id, cols[best], threshold)
-            n_left = sess.split(buffer, start, n, cols[best], threshold)
-            if n_left != int(left.sum()):
-                raise _lib.B200Error("row split and threshold counts disagree")
+            n_left = sess.split(buffer, start, n, cols[best], threshold, expected=int(left.sum()))
             pending.append((start + n_left, n - n_left, buffer ^ 1, counts - left, node_id, False, depth + 1))
             pending.append((start, n_left, buffer ^ 1, left, node_id, True, depth + 1))
     finally:
@@ -175,9 +179,7 @@ def grow_random_regression(tree, X, y, max_depth, max_feature, min_improvement, 
                 tree.add_leaf(node_id, node[0] / n)       # leaf_from_data_regression: np.mean (tree_builder.py:16-17)
                 continue
             tree.add_binary_v2(node_id, cols[best], threshold)
-            n_left = sess.split(buffer, start, n, cols[best], threshold)
-            if n_left != n_left_expected:
-                raise _lib.B200Error("row split and threshold counts disagree")
+            n_left = sess.split(buffer, start, n, cols[best], threshold, expected=n_left_expected)
             pending.append((start + n_left, n - n_left, buffer ^ 1, node_id, False, depth + 1))
             pending.append((start, n_left, buffer ^ 1, node_id, True, depth + 1))
     finally:
