@@ -68,6 +68,24 @@ def _worker(rank, world, port, out):
                 mask |= torch.from_numpy(bits.view(np.int32))
         reduce_side_mask(mask, world)
         assert np.array_equal(mask.numpy().view(np.uint32), expect), "SUM of disjoint masks must equal OR"
+        # the totals round of the sharded exact search (include/b200dt.h, b200dt_session_begin): every rank emits a
+        # record marked exact == 2; only the owner of the last global column (f == F - 1) carries the node total
+        F = 10
+        lo, hi = shard_columns(F, world, rank)
+        owner = hi == F
+        tot = np.zeros(N_NODES, dtype=mine.dtype)
+        for node in range(N_NODES):
+            tot[node] = (0.0, 0.0, 100.0 + node if owner else 0.0, 0.0, 0.0, -1, F - 1 if owner else -1, 2, 0)
+        g2 = gather_candidates(torch.from_numpy(tot.view(np.uint8).copy()), world).numpy().view(mine.dtype)
+        g2 = g2.reshape(world, N_NODES)
+        totals = []
+        for node in range(N_NODES):
+            recs = [g2[r][node] for r in range(world)]
+            assert all(int(c["exact"]) == 2 for c in recs)
+            have = [float(c["left_sum"]) for c in recs if int(c["f"]) == F - 1]
+            assert len(have) == 1, "exactly one rank owns the last global column"
+            totals.append(have[0])
+        assert totals == [100.0 + node for node in range(N_NODES)]
         out[rank] = winners
     finally:
         dist.destroy_process_group()
