@@ -1176,7 +1176,7 @@ static int class_partition(b200dt_ctx *ctx, const u32 *d_mask, const int *d_lcou
             sg.pstep = 1;
             sg.pside = 0;
             sg.vstart = -1;
-            sg.vpad = 0;
+            sg.cbase = 0;
             const int si = (int)psegs.size();
             psegs.push_back(sg);
             for (int t = 0; t < sg.np; ++t) ptiles.push_back(TileDesc{si, t});

@@ -457,6 +457,7 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
     tiles.clear();
     small.clear();
     tile_elems = small_elems = 0;
+    std::vector<int> scanned;   // live nodes searched by the tiled scan
     // candidate slots: [0, fused_slots) were written by the fused level kernel of the parents; behind
     // them every live node reserves slots of its own (its tiles when it must be scanned here -- the
     // root, or any node of a gather-path session -- else one, for the sequential search)
@@ -478,7 +479,7 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
         sg.pstep = 1;
         sg.pside = 0;
         sg.vstart = -1;
-        sg.vpad = 0;
+        sg.cbase = 0;
         sg.pbase = pbase;
         sg.np = sg.exact ? 1 : ntiles;
         const bool from_parent = nd.has_fused && !sg.exact;
@@ -497,9 +498,25 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
                 small_elems += nd.n;
             }
         } else if (!only_forced && !from_parent) {
-            for (int t = 0; t < sg.np; ++t) tiles.push_back(TileDesc{i, t});
+            scanned.push_back(i);
             tile_elems += nd.n;
         }
+    }
+    // Tile order of the scan: ROUND-ROBIN over the nodes (tile 0 of every node, then tile 1 of every node, ...).  A
+    // persistent grid has a fixed number of tiles in flight; in node-major order they would all be consecutive tiles
+    // of ONE (node, column) chain when a rank owns few columns (~110 at 32 columns), and every look-back then waits
+    // for the slowest of ~110 predecessors.  Interleaving the nodes divides that by the number of live nodes.  A tile
+    // still only depends on lower-numbered tiles of its own chain.
+    {
+        int max_np = 0, cbase = 0;
+        for (int i : scanned) {
+            max_np = std::max(max_np, s->h_segs[i].np);
+            s->h_segs[i].cbase = cbase;    // chain slots stay node-major, only the processing order is interleaved
+            cbase += s->h_segs[i].np;
+        }
+        for (int t = 0; t < max_np; ++t)
+            for (int i : scanned)
+                if (t < s->h_segs[i].np) tiles.push_back(TileDesc{i, t});
     }
     CKR(scratch_get(ctx, SB_SEG, (size_t)n_live * sizeof(SegDev) + 64, (void **)&s->d_segs));
     CKR(scratch_get(ctx, SB_PARTIAL, (size_t)(pbase + 1) * s->F_local * sizeof(Partial) + 64, (void **)&s->d_partials));
@@ -765,7 +782,7 @@ static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gather
             sg.pstep = 1;
             sg.pside = 0;
             sg.vstart = -1;
-            sg.vpad = 0;
+            sg.cbase = 0;
             const int si = (int)s->plan_segs.size();
             s->plan_segs.push_back(sg);
             for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{si, t});
@@ -1470,7 +1487,7 @@ int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64
     sg.pstep = 1;
     sg.pside = 0;
     sg.vstart = -1;
-    sg.vpad = 0;
+    sg.cbase = 0;
     s->plan_segs.assign(1, sg);
     s->plan_tiles.clear();
     for (int t = 0; t < sg.np; ++t) s->plan_tiles.push_back(TileDesc{0, t});

@@ -683,7 +683,7 @@ int l1_level_search(b200dt_ctx *ctx, Session *s, b200dt_candidate *d_out, bool e
         sg.pstep = 1;
         sg.pside = 0;
         sg.vstart = -1;
-        sg.vpad = 0;
+        sg.cbase = 0;
         s->h_segs[i] = sg;
         max_n = std::max(max_n, nd.n);
         n_elems += nd.n;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_kernel(LevelArgs a, const Tile
         double texcl = shfl_up_d(incl, 1);
         if (lane == 0) texcl = 0.0;
         const double tile_total = shfl_d(incl, 31);
-        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + sg.cbase + td.tin, td.tin, epoch, tile_total, lane);
         const double offset = excl + texcl;
 
         // score of every position of this lane; best and runner-up tracked branch-free
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
             if (lane >= d) incl += o;
         }
         const double tile_total = shfl_d(incl, 31);
-        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + sg.cbase + td.tin, td.tin, epoch, tile_total, lane);
         double S = excl + (incl - tsum);   // sum of everything before this lane's first position
 
         const int n = sg.n;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 3) l2_scan_bulk_kernel(LevelA
             if (lane >= d) incl += x;
         }
         const double tile_total = shfl_d(incl, 31);
-        const double excl = lookback_f64(st, (int64_t)f * n_tiles + ti, td.tin, epoch, tile_total, lane);
+        const double excl = lookback_f64(st, (int64_t)f * n_tiles + sg.cbase + td.tin, td.tin, epoch, tile_total, lane);
         double S = excl + (incl - tsum);   // sum of everything before this lane's first position
 
         const double mean = sg.total * rcp_fast1((double)n);

@@ -27,7 +27,9 @@ struct SegDev {
     int pstep;      // candidate slot j of this node is pbase + j * pstep + pside: (1, 0) for slots of
     int pside;      // its own; (2, side) when the fused level kernel scored it from its parent's tiles
     int vstart;     // >= 0: the node's rows still lie inside its PARENT's segment, which starts here (two-level
-    int vpad;       // search: candidates then carry Partial::ppos); -1: [start, start+n) is physical
+    int cbase;      // search: candidates then carry Partial::ppos); -1: [start, start+n) is physical.  cbase: first
+                    // look-back chain slot of this node (its tiles own slots cbase .. cbase + np - 1 of every column,
+                    // whatever order the tiles are processed in)
 };
 
 // One split node handed to the fused level kernel (partition + search of the children).

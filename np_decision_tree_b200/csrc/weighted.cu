@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 3) l2w_scan_stream_kernel(LevelArgs a, co
         tile.c = 0;
         tile.l = shfl_d(iy, 31);
         tile.r = shfl_d(iw, 31);
-        const Carry3 pre = lookback3(status, (int64_t)f * n_tiles + ti, td.tin, epoch, tile, lane);
+        const Carry3 pre = lookback3(status, (int64_t)f * n_tiles + sg.cbase + td.tin, td.tin, epoch, tile, lane);
         double Sy = pre.l + (iy - ts_y), Sw = pre.r + (iw - ts_w);
         const int n = sg.n;
         const double Ty = sg.total, Tw = sg.total_w;
