@@ -316,3 +316,27 @@ def test_bulk_copy_scan_builds_the_same_tree(monkeypatch, seed, n, F, depth, yr,
     X, y = small_problem(seed, n, F, yr)
     want = oracle.fit_l2(X, y, max_depth=depth, v=v, sort_kind="stable")
     assert_same_tree(one.build_regression_tree(X, y, max_depth=depth, v=v), want, what=f"bulk scan seed {seed}")
+
+
+def test_pageable_strided_host_input_takes_the_bounce_pipeline(dt):
+    """>= 64 MB of ordinary (pageable) host memory with a row stride larger than F: packed into pinned slots by host
+    threads, column batch by column batch (csrc/fit.cu: bounce_start) -- same tree as the contiguous / device paths."""
+    import ctypes
+    import torch
+    from np_decision_tree_b200.decision_tree.one import DecisionTree
+    rs = np.random.RandomState(91)
+    wide = rs.standard_normal((300000, 48))
+    F, ldx, depth = 40, 48, 6
+    Xv = wide[:, 5:5 + F]                       # a view: rows 48 doubles apart
+    y = Xv[:, 3] * 20.0 - Xv[:, 17] * 7.0 + 0.5 * rs.standard_normal(300000)
+    want = dt.one.build_regression_tree(torch.from_numpy(np.ascontiguousarray(Xv)).cuda(), torch.from_numpy(y).cuda(),
+                                        max_depth=depth)
+    tree = DecisionTree(2 ** (depth + 1))
+    t = tree.tree_
+    count = ctypes.c_int64()
+    ctx = dt.ctx
+    ctx.check(ctx.lib.b200dt_fit(ctx.handle, wide.ctypes.data + 5 * 8, y.ctypes.data, 300000, F, ldx, 0, 0, depth, 1e-7, 1, 1,
+                                 t.children_left.ctypes.data, t.children_right.ctypes.data, t.feature.ctypes.data,
+                                 t.threshold.ctypes.data, t.value.ctypes.data, t.feature.shape[0], ctypes.byref(count)))
+    tree.max_node_ = int(count.value) - 1
+    assert_same_tree(tree, want, leaf_rtol=1e-12, what="strided pageable input")
