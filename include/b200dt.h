@@ -87,6 +87,12 @@ int b200dt_l2_score_cumsums(b200dt_ctx *ctx, const double *cumsums, int64_t n, i
 int b200dt_l1_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F,
                          const double *X, int64_t ldx, const double *y, int64_t N,
                          int64_t *out_k, int64_t *out_f, double *out_cost, double *out_threshold);
+/* replaces: best_l1_improvements / best_l1_improvements_v2(ys) as stand-alone functions   ref strategy_l1.py:49-122
+ * ys: (n, F) float64 row-major HOST matrix whose columns are searched independently (they need not be permutations
+ * of one another); all F columns go through one batched search.  Flat row-major argmin: lowest cost, then lowest
+ * row, then lowest column. */
+int b200dt_l1_best_columns(b200dt_ctx *ctx, const double *ys, int64_t n, int64_t F, int64_t *out_k, int64_t *out_f,
+                           double *out_cost);
 /* replaces: np_stream_median.cummedian(arr)               ref np_stream_median.pyx:8-39
  *           StreamMedian.__call__                          ref stream_median.py:90-92
  * out: (n, 2) float64 (lower, upper) median of a[0..i]. */

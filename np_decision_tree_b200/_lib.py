@@ -50,6 +50,8 @@ _SIGNATURES = {
     "b200dt_l1_split_node": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                      ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
+    "b200dt_l1_best_columns": (c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                       ctypes.POINTER(c_dbl)]),
     "b200dt_cummedian": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int]),
     "b200dt_split_orders": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "b200dt_fit": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_i64,

@@ -1460,6 +1460,95 @@ int b200dt_l1_split_node(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int6
     return r;
 }
 
+// replaces: best_l1_improvements[_v2](ys) as a stand-alone function of an (n, F) matrix whose columns need not be
+// permutations of one another                                                     ref strategy_l1.py:49-122
+// Every column is its own one-feature problem; all F of them are searched in ONE level of a throw-away session:
+// row f*n + i holds ys[i, f], node f is the segment [f*n, (f+1)*n) of a single feature column in identity order.
+int b200dt_l1_best_columns(b200dt_ctx *ctx, const double *ys, int64_t n, int64_t F, int64_t *out_k, int64_t *out_f,
+                           double *out_cost) {
+    if (!ctx) return 1;
+    if (!ys || !out_k || !out_f || !out_cost) return ctx->fail_msg("l1_best_columns: null argument");
+    if (n < 2 || F < 1) return ctx->fail_msg("l1_best_columns: attempt to get argmin of an empty sequence (n < 2)");
+    const int64_t NN = n * F;
+    if (NN >= (1ll << 30)) return ctx->fail_msg("l1_best_columns: n * F must be < 2^30");
+    CK(cudaSetDevice(ctx->device));
+    end_all_sessions(ctx);
+    Session *s = new (std::nothrow) Session();
+    if (!s) return ctx->fail_msg("out of host memory");
+    ctx->session = s;
+    s->N = NN;
+    s->F_local = s->F_global = 1;
+    s->F_store = 2;
+    s->total_col = 0;
+    s->ycol = 1;
+    s->criterion = B200DT_L1;
+    s->variant = 1;
+    s->max_depth = 1;
+    s->col_stride = (NN + 31) / 32 * 32;
+    std::vector<double> yy((size_t)NN);
+    std::vector<int> h((size_t)2 * s->col_stride, 0);
+    for (int64_t f = 0; f < F; ++f) {
+        double *yc = yy.data() + f * n;
+        for (int64_t i = 0; i < n; ++i) yc[i] = ys[i * F + f];
+        int *idc = h.data() + f * n, *ysorted = h.data() + s->col_stride + f * n;
+        for (int64_t i = 0; i < n; ++i) idc[i] = ysorted[i] = (int)(f * n + i);
+        std::stable_sort(ysorted, ysorted + n, [&](int a, int b) { return yy[a] < yy[b]; });
+    }
+    CKR(scratch_get(ctx, SB_ORD_A, h.size() * 4, (void **)&s->ord[0]));
+    CKR(scratch_get(ctx, SB_ORD_B, h.size() * 4, (void **)&s->ord[1]));
+    double *dy;
+    CKR(scratch_get(ctx, SB_Y, (size_t)NN * 8, (void **)&dy));
+    CK(cudaMemcpyAsync(s->ord[0], h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy, yy.data(), (size_t)NN * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    s->dX = nullptr;
+    s->ldx = 1;
+    s->dy = dy;
+    CKR(scratch_get(ctx, SB_MASK, (size_t)((NN + 31) / 32) * 4 + 64, (void **)&s->d_own_mask));
+    for (int64_t f = 0; f < F; ++f) {
+        HNode nd;
+        nd.start = (int)(f * n);
+        nd.n = (int)n;
+        s->nodes.push_back(nd);
+        s->live.push_back((int)f);
+    }
+    s->force_exact.assign(s->live.size(), 0);
+    s->known_total.assign(s->live.size(), 0.0);
+    s->has_total.assign(s->live.size(), 0);
+    b200dt_candidate *d_c;
+    CKR(scratch_get(ctx, SB_RESULT, (size_t)F * sizeof(b200dt_candidate) + 64, (void **)&d_c));
+    std::vector<b200dt_candidate> hc((size_t)F);
+    for (int round = 0; round < 2; ++round) {
+        CKR(session_search_impl(ctx, d_c, round == 1));
+        CK(cudaMemcpyAsync(hc.data(), d_c, (size_t)F * sizeof(b200dt_candidate), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool again = false;
+        for (int64_t f = 0; f < F; ++f) {
+            const b200dt_candidate &c = hc[f];
+            if (!c.exact && c.gain2 >= c.gain - NEAR_TIE_EPS * std::fabs(c.gain)) {
+                s->force_exact[f] = 1;   // a near tie of a chunked (parallel-order) cost sum: redo sequentially
+                again = true;
+            }
+        }
+        if (!again) break;
+    }
+    // flat row-major argmin of the reference (strategy_l1.py:120-121): lowest cost, then lowest row, then lowest column
+    int64_t bf = -1;
+    for (int64_t f = 0; f < F; ++f) {
+        if (hc[f].k < 0) continue;
+        if (bf < 0 || hc[f].gain > hc[bf].gain || (hc[f].gain == hc[bf].gain && hc[f].k < hc[bf].k)) bf = f;
+    }
+    if (bf < 0) {
+        session_free(ctx);
+        return ctx->fail_msg("l1_best_columns: no candidate");
+    }
+    *out_k = hc[bf].k;
+    *out_f = bf;
+    *out_cost = -hc[bf].gain;
+    session_free(ctx);
+    return 0;
+}
+
 int b200dt_split_orders(b200dt_ctx *ctx, const int64_t *orders, int64_t n, int64_t F, const int64_t *left_rows,
                         int64_t n_left, int64_t n_samples, int64_t *left_out, int64_t *right_out) {
     CK(cudaSetDevice(ctx->device));

@@ -41,25 +41,17 @@ def best_l1_improvements_v2(ys):
     """(row, column, children L1 cost) of the best split of ``ys`` (n, F) (strategy_l1.py:87-122).
     The cost is minimised; ties go to the lowest row, then the lowest column (flat argmin).
 
-    The columns of an arbitrary ``ys`` need not be permutations of one another, so each column
-    is searched as its own one-feature node (its own y ranks) and the winners are combined
-    with the reference's tie rule."""
+    The columns of an arbitrary ``ys`` need not be permutations of one another, so each column is its own
+    one-feature problem; all F of them are searched in one batched call (``b200dt_l1_best_columns``)."""
     ys = np.ascontiguousarray(ys, dtype=np.float64)
+    if ys.ndim != 2:
+        raise ValueError("ys must be (n, F)")
     n, F = ys.shape
     ctx = context_for()
-    orders = np.arange(n, dtype=np.int64).reshape(n, 1)
-    best = None
-    for f in range(F):
-        y = np.ascontiguousarray(ys[:, f])
-        k, ff = ctypes.c_int64(), ctypes.c_int64()
-        cost, thr = ctypes.c_double(), ctypes.c_double()
-        ctx.check(ctx.lib.b200dt_l1_split_node(ctx.handle, orders.ctypes.data, n, 1, None, 0, y.ctypes.data, n,
-                                               ctypes.byref(k), ctypes.byref(ff), ctypes.byref(cost),
-                                               ctypes.byref(thr)))
-        cand = (cost.value, k.value, f)
-        if best is None or cand < best:
-            best = cand
-    return best[1], best[2], best[0]
+    k, f, cost = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    ctx.check(ctx.lib.b200dt_l1_best_columns(ctx.handle, ys.ctypes.data, n, F, ctypes.byref(k), ctypes.byref(f),
+                                             ctypes.byref(cost)))
+    return k.value, f.value, cost.value
 
 
 best_l1_improvements = best_l1_improvements_v2   # strategy_l1.py:49-84: same results, pure Python there

@@ -119,3 +119,18 @@ def test_l1_leaf_rule_quirk(l1):
     t = l1.l1.build_regression_tree_v2(X, y, max_depth=12)
     o = oracle.fit_l1(X, y, max_depth=12, sort_kind="stable")
     assert_same_tree(t, o)
+
+
+@pytest.mark.parametrize("n,F,seed,yr", [(2, 3, 1, None), (257, 9, 2, 5.0), (5000, 4, 3, None), (70000, 3, 4, None)])
+def test_best_l1_improvements_independent_columns(l1, n, F, seed, yr):
+    """ys with ARBITRARY columns (not permutations of one another): every column is its own problem, searched in one
+    batched call; the flat argmin (lowest cost, lowest row, lowest column) follows strategy_l1.py:119-121."""
+    rs = np.random.RandomState(seed)
+    ys = rs.standard_normal((n, F)) * rs.uniform(0.5, 20.0, size=(1, F))
+    if yr:
+        ys = np.round(ys * yr) / yr
+    ys[:, F - 1] = ys[:, 0]                                     # two identical columns: the lower index must win ties
+    k, f, c = l1.l1.best_l1_improvements_v2(ys)
+    ok, of, oc = oracle.l1_best_split(ys)
+    assert (k, f) == (ok, of)
+    assert c == pytest.approx(float(oc), rel=RTOL, abs=1e-12)
