@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -171,6 +172,13 @@ static inline int pinned_get(b200dt_ctx *ctx, int slot, size_t bytes, void **out
     *out = ctx->pinned[slot];
     return 0;
 }
+
+// NVTX range around a host-side phase (sort, level search / decide / partition, predict): shows up in Nsight
+// timelines; header-only, a no-op without a profiler attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------
 // launch bracket: counts launches; with profiling on, times them with events

@@ -275,6 +275,7 @@ static int session_begin_impl(b200dt_ctx *ctx, const double *X, const double *y,
                               int64_t ldx, int space, int criterion, int max_depth, double min_improvement,
                               int64_t min_sample_leaf, int variant, int64_t col_offset, int64_t F_global,
                               const double *last_col, int64_t last_col_ld, const double *weight = nullptr) {
+    NvtxRange nvtx("b200dt: begin (H2D + sort)");
     if (N <= 0 || F_local <= 0) return ctx->fail_msg("fit: empty input");
     if (N >= (1ll << 30)) return ctx->fail_msg("fit: N must be < 2^30");
     if (F_local > 65534) return ctx->fail_msg("fit: at most 65534 columns per GPU (shard the columns over more ranks)");
@@ -529,6 +530,7 @@ static int upload_level(b200dt_ctx *ctx, Session *s, std::vector<TileDesc> &tile
 static int materialise_pending(b200dt_ctx *ctx);
 
 static int session_search_impl(b200dt_ctx *ctx, b200dt_candidate *d_out, bool exact_only) {
+    NvtxRange nvtx(exact_only ? "b200dt: level search (exact)" : "b200dt: level search");
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     const int n_live = (int)s->live.size();
@@ -645,6 +647,7 @@ static bool cand_better(const b200dt_candidate &b, const b200dt_candidate &a, bo
 
 static int session_decide_impl(b200dt_ctx *ctx, const b200dt_candidate *d_gathered, int n_ranks, u32 *d_mask,
                                int *need_partition, int *need_exact) {
+    NvtxRange nvtx("b200dt: level decide");
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     *need_partition = 0;
@@ -924,6 +927,7 @@ static int materialise_pending(b200dt_ctx *ctx) {
 }
 
 static int session_partition_impl(b200dt_ctx *ctx, const u32 *d_mask) {
+    NvtxRange nvtx("b200dt: level partition");
     Session *s = ctx->session;
     if (!s) return ctx->fail_msg("session: not begun");
     if (s->plan_segs.empty()) return 0;
@@ -1619,6 +1623,7 @@ int b200dt_predict(b200dt_ctx *ctx, const double *X, int64_t N, int64_t F, int64
                    const int64_t *feature, const double *threshold, const int64_t *children_left,
                    const int64_t *children_right, const double *value, int64_t n_nodes, double *out_value,
                    int32_t *out_leaf, int out_space) {
+    NvtxRange nvtx("b200dt: predict");
     CK(cudaSetDevice(ctx->device));
     if (N <= 0) return 0;
     if (n_nodes <= 0 || n_nodes > (1ll << 30)) return ctx->fail_msg("predict: bad node count");

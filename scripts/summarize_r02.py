@@ -70,11 +70,12 @@ with open(os.path.join(out_dir, f"{tag}_launch_list_summary.md"), "w") as f:
     for k, (n, us, b) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {n} | {us / 1e3:.2f} | {us / total:.3f} | {b / 1e9:.2f} |\n")
     f.write(f"\nTotal {total / 1e3:.1f} ms over {sum(e[0] for e in per.values())} launches.\n")
-with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
-    f.write("index,kernel,duration_us,dram_bytes\n")
+with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow(["index", "kernel", "duration_us", "dram_bytes"])
     for i, d in enumerate(step):
-        f.write(f"{i},{d['kernel']},{d['gpu__time_duration.sum']:.3f},"
-                f"{d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0):.0f}\n")
+        w.writerow([i, d["kernel"], f"{d['gpu__time_duration.sum']:.3f}",
+                    f"{d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0):.0f}"])
 tj = {c: {"bytes_per_step": v[0], "launches_per_step": v[1]} for c, v in cls_bytes.items()}
 json.dump(tj, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, f"{tag}_launch_list_summary.md")).read())
