@@ -176,8 +176,7 @@ static int bounce_start(b200dt_ctx *ctx, std::unique_ptr<BouncePipe> &pipe, cons
         c0 = (int64_t)b * h2d_cols;
         fb = std::min<int64_t>(h2d_cols, F_local - c0);
     };
-    for (int w = 0; w < workers; ++w)
-        bp->threads.emplace_back([=]() {
+    auto packer = [=]() {
             cudaSetDevice(device);
             while (true) {
                 const int i = bp->next.fetch_add(1);
@@ -202,8 +201,8 @@ static int bounce_start(b200dt_ctx *ctx, std::unique_ptr<BouncePipe> &pipe, cons
                 }
                 bp->cv.notify_all();
             }
-        });
-    bp->threads.emplace_back([=]() {   // feeder: copies leave in item order, one event per column batch
+        };
+    auto feeder = [=]() {   // feeder: copies leave in item order, one event per column batch
         cudaSetDevice(device);
         for (int i = 0; i < n_items; ++i) {
             {
@@ -234,7 +233,27 @@ static int bounce_start(b200dt_ctx *ctx, std::unique_ptr<BouncePipe> &pipe, cons
         }
         cudaStreamSynchronize(cs);   // the slots are reused by the next fit
         for (auto ev : slot_ev) cudaEventDestroy(ev);
-    });
+    };
+    // thread creation can fail (resource limits): the feeder is indispensable, the packers degrade gracefully
+    int started = 0;
+    try {
+        bp->threads.emplace_back(feeder);
+        for (int w = 0; w < workers; ++w) {
+            bp->threads.emplace_back(packer);
+            ++started;
+        }
+    } catch (const std::exception &) {
+    }
+    if (started == 0) {
+        {
+            std::lock_guard<std::mutex> lk(bp->m);
+            bp->failed = true;
+            bp->err = "pageable H2D pipeline: could not start host threads";
+        }
+        bp->cv.notify_all();
+        pipe.reset();   // joins whatever was started
+        return ctx->fail_msg("pageable H2D pipeline: could not start host threads");
+    }
     return 0;
 }
 
