@@ -114,6 +114,18 @@ def load():
         if _lib is not None:
             return _lib
         path = LIB_PATH
+        variant = os.environ.get("B200DT_LIB")
+        if variant:
+            # developer override: another build of the same sources (kernel tuning experiments, scripts/build_variant.sh)
+            if not os.path.exists(variant):
+                raise B200Error(f"B200DT_LIB={variant} does not exist")
+            lib = ctypes.CDLL(variant)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+            return lib
         if os.environ.get("B200DT_CHECKED") == "1":
             # the bounds-checked build (`python -m np_decision_tree_b200._build --checked`): every hot kernel asserts
             # its indices on the device and traps with a message; used where compute-sanitizer is not available

@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(256, 3) partition4_kernel(const int *__restric
         const int cnt = min(P4_TILE, sg.n - off);
         const int64_t cbase = (int64_t)f * col_stride + sg.start;
         const int *col = in + cbase + off;
-        int rows[PT_ITEMS];
+        int rows[P4_ITEMS];
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
+        for (int i = 0; i < P4_ITEMS; ++i) rows[i] = (i * 32 + lane < cnt) ? ld_stream_i32(col + i * 32 + lane) : -1;
         u32 abits = 0, bbits = 0;   // bit i: item i of this lane
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) {
+        for (int i = 0; i < P4_ITEMS; ++i) {
             const int row = rows[i];
             const u32 code = row >= 0 ? ((__ldg(codes + (row >> 4)) >> ((row & 15) * 2)) & 3u) : 0u;
             abits |= (code & 1u) << i;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256, 3) partition4_kernel(const int *__restric
         }
         int c_ll = 0, c_lr = 0, c_rl = 0;
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) {
+        for (int i = 0; i < P4_ITEMS; ++i) {
             const bool ok = i * 32 + lane < cnt;
             const bool A = (abits >> i) & 1u, B = (bbits >> i) & 1u;
             c_ll += __popc(__ballot_sync(FULL_MASK, ok && A && B));
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, 3) partition4_kernel(const int *__restric
         const double *ycol = y_in + cbase + off;
         double *oy = y_out + cbase;
 #pragma unroll
-        for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
+        for (int i0 = 0; i0 < P4_ITEMS; i0 += 4) {
             double yv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

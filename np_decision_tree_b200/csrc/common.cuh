@@ -6,6 +6,7 @@
 #include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -214,10 +215,12 @@ struct LaunchScope {
 };
 
 static inline void prof_drain(b200dt_ctx *ctx) {
+    static const bool trace = getenv("B200DT_TRACE_LAUNCHES") != nullptr;   // one line per bracket on stderr
     for (auto &s : ctx->prof_pending) {
         cudaEventSynchronize(s.b);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, s.a, s.b);
+        if (trace) fprintf(stderr, "b200dt launch class %d: %.3f ms\n", s.kc, ms);
         ctx->prof_ms[s.kc] += ms;
         ctx->prof_free.push_back(s.a);
         ctx->prof_free.push_back(s.b);
@@ -273,6 +276,11 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 __device__ __forceinline__ int ld_stream_i32(const int *p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {

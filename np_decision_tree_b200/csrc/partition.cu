@@ -39,16 +39,24 @@ __global__ void __launch_bounds__(256) mark_left_kernel(const int *__restrict__ 
 // RELABEL: this level also hands out the new, node-contiguous row ids (relabel.cu): the look-up reads the
 // row's new id instead of its side bit, the side is `new id < first id of the right child`, and the new id
 // is what gets written.
+#ifndef PT_YG
+#define PT_YG 8
+#endif
+constexpr int PT_THREADS = 32 * PT_WARPS;
+// y (PAY == 1) is requested PT_YG items at a time AFTER the look-back.  Measured (profiles/r02_partition_variants.md):
+// 8 at a time beats 4 (13.4 vs 14.2 ms per level, 16 spill bytes); anything that requests y EARLIER is slower -- the
+// first group before the barrier (15.1 ms), all of it with the row ids (8 items x 16 warps: 16.5 ms), or a bulk
+// asynchronous copy into shared memory at the start of the tile (17 ms).
+
 template <int PAY, bool RELABEL>
-__global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict__ in, int *__restrict__ out,
-                                                           const double *__restrict__ y_in, double *__restrict__ y_out,
-                                                           const double *__restrict__ w_in, double *__restrict__ w_out,
-                                                           int64_t col_stride, const SegDev *__restrict__ segs,
-                                                           const TileDesc *__restrict__ tiles, int n_tiles,
-                                                           const u32 *__restrict__ mask, u64 *status, u32 epoch,
-                                                           int n_cols, int row_mask, const int *__restrict__ newid) {
-    __shared__ int s_cnt[2][8];
+__global__ void __launch_bounds__(PT_THREADS, 1024 / PT_THREADS) partition_kernel(
+    const int *__restrict__ in, int *__restrict__ out, const double *__restrict__ y_in, double *__restrict__ y_out,
+    const double *__restrict__ w_in, double *__restrict__ w_out, int64_t col_stride, const SegDev *__restrict__ segs,
+    const TileDesc *__restrict__ tiles, int n_tiles, const u32 *__restrict__ mask, u64 *status, u32 epoch, int n_cols,
+    int row_mask, const int *__restrict__ newid) {
+    __shared__ int s_cnt[2][PT_WARPS];
     __shared__ int s_excl[2];
+    constexpr int YG = PAY == 1 ? PT_YG : 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
     const int64_t total_tiles = (int64_t)n_tiles * n_cols;
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         const int cnt = max(0, min(PT_WARP, sg.n - off));     // 0: this warp's part lies beyond the node's end
         const int64_t cbase = (int64_t)f * col_stride + sg.start;
         const int *col = in + cbase + off;
+        const double *ycol = (PAY == 1 || PAY == 2) ? y_in + cbase + off : nullptr;
         int rows[PT_ITEMS];
         if (cnt == PT_WARP) {
 #pragma unroll
@@ -95,38 +104,36 @@ __global__ void __launch_bounds__(256, 4) partition_kernel(const int *__restrict
         if (lane == 0) s_cnt[par][warp] = run;
         __syncthreads();
         if (warp == 0) {
-            int total = lane < 8 ? s_cnt[par][lane] : 0;
+            int total = lane < PT_WARPS ? s_cnt[par][lane] : 0;
 #pragma unroll
-            for (int m = 4; m >= 1; m >>= 1) total += __shfl_xor_sync(FULL_MASK, total, m);
-            total = __shfl_sync(FULL_MASK, total, 0);
+            for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(FULL_MASK, total, m);
             const int excl = lookback_count(status, (int64_t)f * n_tiles + ti, td.tin, epoch, total, lane);
             if (lane == 0) s_excl[par] = excl;
         }
         __syncthreads();
         int lb_row = s_excl[par];     // left rows of the node before this warp's first position
 #pragma unroll
-        for (int w = 0; w < 7; ++w) lb_row += w < warp ? s_cnt[par][w] : 0;
+        for (int w = 0; w < PT_WARPS - 1; ++w) lb_row += w < warp ? s_cnt[par][w] : 0;
         // (the slots of this parity are rewritten two tiles later, after every warp has passed the barriers of the
         // next tile, i.e. after these reads)
         int *ocol = out + cbase;
-        const double *ycol = (PAY == 1 || PAY == 2) ? y_in + cbase + off : nullptr;
         double *oy = (PAY == 1 || PAY == 2) ? y_out + cbase : nullptr;
         const double *wcol = PAY == 2 ? w_in + cbase + off : nullptr;
         double *ow = PAY == 2 ? w_out + cbase : nullptr;
         if (cnt > 0) {
 #pragma unroll
-            for (int i0 = 0; i0 < PT_ITEMS; i0 += 4) {
-                double yv[4], wv[4];
+            for (int i0 = 0; i0 < PT_ITEMS; i0 += YG) {
+                double yv[YG], wv[YG];
                 if (PAY == 1 || PAY == 2) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < YG; ++u) {
                         const int e = (i0 + u) * 32 + lane;
-                        yv[u] = e < cnt ? __ldcs(ycol + e) : 0.0;
+                        yv[u] = e < cnt ? ld_stream_f64(ycol + e) : 0.0;
                         if (PAY == 2) wv[u] = e < cnt ? __ldcs(wcol + e) : 0.0;
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < YG; ++u) {
                     const int i = i0 + u;
                     const u32 b = __ballot_sync(FULL_MASK, (leftbits >> i) & 1u);
                     const int e = i * 32 + lane;
@@ -207,7 +214,7 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
                        : pay == 2 ? (newid ? (const void *)partition_kernel<2, true> : (const void *)partition_kernel<2, false>)
                        : pay == 1 ? (newid ? (const void *)partition_kernel<1, true> : (const void *)partition_kernel<1, false>)
                                   : (const void *)partition_kernel<0, false>;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > total) grid = total;
     LaunchScope ls(ctx, KC_PARTITION, 9.0 * (double)n_elems * F_store);
@@ -215,6 +222,6 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
     double *yo = (pay == 1 || pay == 2) ? y_out : nullptr, *wo = pay == 2 ? w_out : nullptr;
     void *args[] = {&orders_in, &orders_out, &yi, &yo, &wi, &wo, &col_stride, &segs, &tiles, &n_tiles, &mask, &status,
                     &epoch, &F_store, &packed_row_mask, &newid};
-    CK(launch_resident(kern, (unsigned)grid, 256, args, 0, ctx->stream));
+    CK(launch_resident(kern, (unsigned)grid, PT_THREADS, args, 0, ctx->stream));
     return 0;
 }

@@ -5,10 +5,18 @@
 // Tiles are owned by single warps (no block barriers anywhere in K2 / K4):
 constexpr int WT_ITEMS = 16;
 constexpr int WT_TILE = 32 * WT_ITEMS;   // K2: 512 sorted positions per warp tile
-constexpr int PT_ITEMS = 16;
+#ifndef PT_ITEMS_CFG
+#define PT_ITEMS_CFG 16
+#endif
+#ifndef PT_WARPS_CFG
+#define PT_WARPS_CFG 8
+#endif
+constexpr int PT_ITEMS = PT_ITEMS_CFG;
+constexpr int PT_WARPS = PT_WARPS_CFG;
 constexpr int PT_WARP = 32 * PT_ITEMS;   // K4: 512 sorted positions per warp ...
-constexpr int PT_TILE = 8 * PT_WARP;     // ... 4096 per block tile (one look-back chain entry)
-constexpr int P4_TILE = 32 * PT_ITEMS;   // 4-way partition of the two-level mode (children.cu): one warp per tile
+constexpr int PT_TILE = PT_WARPS * PT_WARP;     // ... 4096 per block tile (one look-back chain entry)
+constexpr int P4_ITEMS = 16;
+constexpr int P4_TILE = 32 * P4_ITEMS;   // 4-way partition of the two-level mode (children.cu): one warp per tile
 constexpr int ST_ITEMS = 32;
 constexpr int ST_TILE = 32 * ST_ITEMS;   // K2 streaming (y payload): 1024 positions per warp tile
 constexpr int EXACT_ROWS = 2048;         // nodes up to this size take the sequential-order search
