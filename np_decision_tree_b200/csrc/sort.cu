@@ -32,7 +32,13 @@
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
+#ifndef RS_ITEMS_CFG
+#define RS_ITEMS_CFG 16
+#endif
+#ifndef RS_MINB_CFG
+#define RS_MINB_CFG 4   // blocks per SM of the 4-byte-key pass (64 registers); 8-byte keys keep 3
+#endif
+constexpr int RS_ITEMS = RS_ITEMS_CFG;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_AGG = 1u << 30;
@@ -250,8 +256,19 @@ __device__ __forceinline__ u64 ld_stream_key<u64>(const u64 *p) { return ld_stre
 template <>
 __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return (u32)ld_stream_i32((const int *)p); }
 
+#define RS_LOAD_VALS()                                                                                              \
+    do {                                                                                                            \
+        if (full) {                                                                                                 \
+            _Pragma("unroll") for (int i = 0; i < RS_ITEMS; ++i)                                                    \
+                val[i] = FIRST ? (int)base + o0 + i * 32 : ld_stream_i32(vin + o0 + i * 32);                        \
+        } else {                                                                                                    \
+            _Pragma("unroll") for (int i = 0; i < RS_ITEMS; ++i)                                                    \
+                val[i] = FIRST ? (int)base + o0 + i * 32 : (o0 + i * 32 < count ? ld_stream_i32(vin + o0 + i * 32) : 0); \
+        }                                                                                                           \
+    } while (0)
+
 template <typename KeyT, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
+__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 3) radix_pass_kernel(
     const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in, KeyT *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
     int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {
@@ -279,15 +296,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
     if (full) {
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) key[i] = ld_stream_key<KeyT>(kin + o0 + i * 32);
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) val[i] = FIRST ? (int)base + o0 + i * 32 : ld_stream_i32(vin + o0 + i * 32);
     } else {
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const bool v = o0 + i * 32 < count;
-            key[i] = v ? ld_stream_key<KeyT>(kin + o0 + i * 32) : (KeyT)~(KeyT)0;
-            val[i] = FIRST ? (int)base + o0 + i * 32 : (v ? ld_stream_i32(vin + o0 + i * 32) : 0);
-        }
+        for (int i = 0; i < RS_ITEMS; ++i)
+            key[i] = o0 + i * 32 < count ? ld_stream_key<KeyT>(kin + o0 + i * 32) : (KeyT)~(KeyT)0;
     }
     // stable rank of each key among the keys of its warp with the same digit.  All peer masks
     // first (independent match.any's pipeline), then, item by item, one shared atomic per distinct
@@ -305,8 +317,18 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
         u32 peers = full ? FULL_MASK : __ballot_sync(FULL_MASK, o0 + i * 32 < count);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            const u32 v = __ballot_sync(FULL_MASK, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? v : ~v;
+            // peers &= bit ? v : ~v in four instructions (LOP3 -> P, VOTE, @!P LOP3, LOP3); the C++ form of the same
+            // line compiled to seven (the predicate was derived twice)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                ".reg .b32 t;\n\t"
+                "and.b32 t, %1, %2;\n\t"
+                "setp.ne.u32 p, t, 0;\n\t"
+                "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"
+                "@!p not.b32 t, t;\n\t"
+                "and.b32 %0, %0, t;\n\t"
+                "}" : "+r"(peers) : "r"(d), "r"(1u << b));
         }
         rank[i] = peers;
     }
@@ -320,6 +342,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
         old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
         rank[i] = old + __popc(below);
     }
+    // the row ids are not needed before the reorder: requested here they travel during the look-back, and the
+    // ranking above runs in 64 registers = 4 blocks per SM (56.0 instead of 62.2 ms for the four 4-byte passes;
+    // an L2 prefetch of these lines at the top of the kernel changes nothing)
+    RS_LOAD_VALS();
     __syncthreads();
     if (tid < 256) {
         // thread `tid` owns digit `tid`: exclusive offsets of the warps, tile total
