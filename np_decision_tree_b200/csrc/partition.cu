@@ -214,6 +214,9 @@ int launch_partition(b200dt_ctx *ctx, const int *orders_in, int *orders_out, int
                        : pay == 2 ? (newid ? (const void *)partition_kernel<2, true> : (const void *)partition_kernel<2, false>)
                        : pay == 1 ? (newid ? (const void *)partition_kernel<1, true> : (const void *)partition_kernel<1, false>)
                                   : (const void *)partition_kernel<0, false>;
+    // the kernel's only use of the unified L1 / shared memory is the side-mask window: ask for all of it as L1
+    // (12.8 instead of 13.3 ms per level)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;  // all blocks resident: tiles wait on earlier tiles
     if (grid > total) grid = total;

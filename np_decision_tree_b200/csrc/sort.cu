@@ -56,7 +56,10 @@ __device__ __forceinline__ int prep_hist_slot(int c, int d, u32 v) {
     return d * (PREP_COLS * 256) + (int)(v >> 2) * (PREP_COLS * 4) + c * 4 + (int)(v & 3u);
 }
 
-constexpr int FIX_TILE = 1024;   // fix-up: positions per block
+#ifndef FIX_TILE_CFG
+#define FIX_TILE_CFG 1024
+#endif
+constexpr int FIX_TILE = FIX_TILE_CFG;   // fix-up: positions per block
 constexpr int FIX_MAX_RUN = 32;  // longest run (equal top-32 bits) repaired in place
 
 // float64 -> uint64 whose unsigned order equals the float order.
