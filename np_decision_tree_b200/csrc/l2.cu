@@ -204,16 +204,45 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
     const double *mine = sy + lane * (ST_ITEMS + 1);   // position lane*32 + j sits at lane*33 + j
     const int64_t total_tiles = (int64_t)n_tiles * a.F_search;
     const int64_t stride_tiles = (int64_t)gridDim.x * 8;
+    // the (tile, node) descriptors of a warp's NEXT tile are fetched while the current tile's y values travel: two
+    // dependent look-ups per tile leave the critical path
+    struct SegLite {
+        double total;
+        int start, n, pbase, pstep, pside, cbase;
+    };
+    auto seg_lite = [&](int seg) {
+        const SegDev *p = a.segs + seg;
+        SegLite l;
+        l.total = p->total;
+        l.start = p->start;
+        l.n = p->n;
+        l.pbase = p->pbase;
+        l.pstep = p->pstep;
+        l.pside = p->pside;
+        l.cbase = p->cbase;
+        return l;
+    };
+    TileDesc td_next{0, 0};
+    SegLite sg_next{};
+    {
+        const int64_t t0 = (int64_t)blockIdx.x * 8 + warp;
+        if (t0 < total_tiles) {
+            td_next = tiles[(int)(t0 / a.F_search)];
+            sg_next = seg_lite(td_next.seg);
+        }
+    }
     for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += stride_tiles) {
-        const int f = (int)(t % a.F_search), ti = (int)(t / a.F_search);
-        const TileDesc td = tiles[ti];
-        const SegDev sg = a.segs[td.seg];
+        const int f = (int)(t % a.F_search);
+        const TileDesc td = td_next;
+        const SegLite sg = sg_next;
         const int off = td.tin * ST_TILE;
         const int cnt = min(ST_TILE, sg.n - off);
         const double *yp = a.ypay + (int64_t)f * a.col_stride + sg.start + off;
         // best gain any warp has found in this node so far (bits of a non-negative double; 0 at level start)
         long long nb_seen = 0;
         if (VARIANT == 1) nb_seen = (long long)ld_relaxed_u64((const u64 *)(a.node_best + td.seg));
+        const bool more = t + stride_tiles < total_tiles;
+        if (more) td_next = tiles[(int)((t + stride_tiles) / a.F_search)];
         if (cnt == ST_TILE) {
 #pragma unroll
             for (int i = 0; i < ST_ITEMS; ++i) sy[i * 33 + lane] = __ldcs(yp + i * 32 + lane);
@@ -224,6 +253,7 @@ __global__ void __launch_bounds__(256, 3) l2_scan_stream_kernel(LevelArgs a, con
                 sy[i * 33 + lane] = e < cnt ? __ldcs(yp + e) : 0.0;
             }
         }
+        if (more) sg_next = seg_lite(td_next.seg);
         __syncwarp();
         double ts0 = 0.0, ts1 = 0.0, ts2 = 0.0, ts3 = 0.0;   // four independent chains (fp64 add latency)
 #pragma unroll

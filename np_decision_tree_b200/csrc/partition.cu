@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1024 / PT_THREADS) partition_kerne
     int par = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, par ^= 1) {
         const int f = (int)(t % n_cols), ti = (int)(t / n_cols);
+        // (fetching the next tile's descriptors early costs registers the kernel does not have: 14.9 vs 12.8 ms)
         const TileDesc td = tiles[ti];
         const SegDev sg = segs[td.seg];
         const int off = td.tin * PT_TILE + warp * PT_WARP;
