@@ -48,12 +48,13 @@ constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
 constexpr int PREP_COLS = 8;     // columns per prepare block: 64-byte row pieces
 constexpr int PREP_ROWS = 256;   // rows per chunk
 constexpr int PREP_PITCH = PREP_ROWS + 4;   // a warp stores 8 columns x 4 rows: word (col * PITCH + row) -> bank 4 col + row
-// Shared-memory slot of histogram bin (column c, digit slot d, value v).  A warp's 32 atomics are 8 columns x 4
-// rows; with the natural [c][d][256] layout the bank is v % 32 whatever the column (3.5 wavefronts per atomic on
-// random digits, 69 % of the kernel's shared-memory wavefronts were bank-conflict replays, ncu r02).  Here column c
-// owns banks 4c .. 4c + 3 of every 32-word row, so only the 4 lanes of one column can collide.
+// Shared-memory slot of histogram bin (column c, digit slot d, value v): [d][v][c].  A warp's 32 atomics are 8
+// columns x 4 rows; with a [c][d][256] layout the bank is v % 32 whatever the column (3.5 wavefronts per atomic on
+// random digits, 69 % of the kernel's shared-memory wavefronts were bank-conflict replays, ncu r02).  Interleaving the
+// columns gives column c the banks c, c + 8, c + 16, c + 24, so only the 4 lanes of one column can collide, and the
+// slot is one scaled add away from the digit.
 __device__ __forceinline__ int prep_hist_slot(int c, int d, u32 v) {
-    return d * (PREP_COLS * 256) + (int)(v >> 2) * (PREP_COLS * 4) + c * 4 + (int)(v & 3u);
+    return (d * 256 + (int)v) * PREP_COLS + c;
 }
 
 #ifndef FIX_TILE_CFG
@@ -193,41 +194,66 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const double *__restr
     rng.scale = 0.0;
     if (sizeof(KeyT) == 4 && tcol < ncols) rng = ranges[cg * PREP_COLS + tcol];
     // software pipeline: the loads of the block's NEXT chunk are in flight while this one is quantised, counted and
-    // written (ncu r02: 22 % of the stall samples sat on the first use of the loaded values, 10 % on the barriers)
-    double xv[PREP_ROWS / 32], xn[PREP_ROWS / 32];
+    // written (ncu r02: 22 % of the stall samples sat on the first use of the loaded values, 10 % on the barriers).
+    // Two register buffers take turns (no copies); once pipelined the kernel is issue-bound (78 %), so the
+    // per-key work is kept short: one shift + one scaled add per histogram slot, no bounds tests in full chunks.
+    const bool active = tcol < ncols;
+    const double *xcol = X + cg * PREP_COLS + tcol;
+    u32 *hmine = hist + tcol;
+    KeyT *tmine = tile + tcol * PREP_PITCH + trow;
     auto load_chunk = [&](int64_t chunk, double (&dst)[PREP_ROWS / 32]) {
         const int64_t r0 = chunk * PREP_ROWS;
+        const double *px = xcol + (r0 + trow) * ldx;
+        if (active && r0 + PREP_ROWS <= N) {
 #pragma unroll
-        for (int it = 0; it < PREP_ROWS / 32; ++it) {
-            const int64_t r = r0 + it * 32 + trow;
-            dst[it] = (r < N && tcol < ncols) ? X[r * ldx + cg * PREP_COLS + tcol] : 0.0;
+            for (int it = 0; it < PREP_ROWS / 32; ++it) dst[it] = px[(int64_t)it * 32 * ldx];
+        } else {
+#pragma unroll
+            for (int it = 0; it < PREP_ROWS / 32; ++it)
+                dst[it] = (active && r0 + it * 32 + trow < N) ? px[(int64_t)it * 32 * ldx] : 0.0;
         }
     };
-    if ((int64_t)blockIdx.x * PREP_ROWS < N) load_chunk(blockIdx.x, xv);
-    for (int64_t chunk = blockIdx.x; chunk * PREP_ROWS < N; chunk += gridDim.x) {
+    auto process_chunk = [&](int64_t chunk, const double (&src)[PREP_ROWS / 32]) {
         const int64_t r0 = chunk * PREP_ROWS;
-        if ((chunk + gridDim.x) * PREP_ROWS < N) load_chunk(chunk + gridDim.x, xn);
+        const int rows_here = (int)min((int64_t)PREP_ROWS, N - r0);
+        if (active) {
 #pragma unroll
-        for (int it = 0; it < PREP_ROWS / 32; ++it) {
-            const int rr = it * 32 + trow;
-            const int64_t r = r0 + rr;
-            if (r < N && tcol < ncols) {
-                const KeyT k = sizeof(KeyT) == 4 ? (KeyT)quantise(xv[it], rng) : narrow_key<KeyT>(sortable_key(xv[it]));
-                tile[tcol * PREP_PITCH + rr] = k;
+            for (int it = 0; it < PREP_ROWS / 32; ++it) {
+                if (rows_here == PREP_ROWS || it * 32 + trow < rows_here) {
+                    const KeyT k = sizeof(KeyT) == 4 ? (KeyT)quantise(src[it], rng) : narrow_key<KeyT>(sortable_key(src[it]));
+                    tmine[it * 32] = k;
 #pragma unroll
-                for (int d = 0; d < NPASS; ++d) atomicAdd(&hist[prep_hist_slot(tcol, d, (u32)((k >> (8 * d)) & 255))], 1u);
+                    for (int d = 0; d < NPASS; ++d)
+                        atomicAdd(hmine + d * (PREP_COLS * 256) + (int)((u32)(k >> (8 * d)) & 255u) * PREP_COLS, 1u);
+                }
             }
         }
         __syncthreads();
-        for (int rr = tid; rr < PREP_ROWS; rr += 256) {
-            if (r0 + rr < N) {
-                for (int j = 0; j < ncols; ++j)
-                    keys[(int64_t)(cg * PREP_COLS + j) * kstride + r0 + rr] = tile[j * PREP_PITCH + rr];
+        if (tid < rows_here) {
+            KeyT *ko = keys + (int64_t)cg * PREP_COLS * kstride + r0 + tid;
+            const KeyT *ti = tile + tid;
+            if (ncols == PREP_COLS) {
+#pragma unroll
+                for (int j = 0; j < PREP_COLS; ++j) ko[(int64_t)j * kstride] = ti[j * PREP_PITCH];
+            } else {
+                for (int j = 0; j < ncols; ++j) ko[(int64_t)j * kstride] = ti[j * PREP_PITCH];
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int it = 0; it < PREP_ROWS / 32; ++it) xv[it] = xn[it];
+    };
+    static_assert(PREP_ROWS == 256, "one output row per thread");
+    double xa[PREP_ROWS / 32], xb[PREP_ROWS / 32];
+    const int64_t n_chunks = (N + PREP_ROWS - 1) / PREP_ROWS;
+    int64_t chunk = blockIdx.x;
+    if (chunk < n_chunks) load_chunk(chunk, xa);
+    while (chunk < n_chunks) {
+        if (chunk + gridDim.x < n_chunks) load_chunk(chunk + gridDim.x, xb);
+        process_chunk(chunk, xa);
+        chunk += gridDim.x;
+        if (chunk >= n_chunks) break;
+        if (chunk + gridDim.x < n_chunks) load_chunk(chunk + gridDim.x, xa);
+        process_chunk(chunk, xb);
+        chunk += gridDim.x;
     }
     for (int i = tid; i < ncols * NPASS * 256; i += 256) {
         const int col = i / (NPASS * 256), rest = i % (NPASS * 256);
