@@ -31,16 +31,27 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 256;           // radix pass, 8-byte keys (4-byte keys: RsCfg below)
 #ifndef RS_ITEMS_CFG
 #define RS_ITEMS_CFG 16
 #endif
-#ifndef RS_MINB_CFG
-#define RS_MINB_CFG 4   // blocks per SM of the 4-byte-key pass (64 registers); 8-byte keys keep 3
+#ifndef RS_THREADS4_CFG
+#define RS_THREADS4_CFG 512   // threads per block of the 4-byte-key pass
 #endif
 constexpr int RS_ITEMS = RS_ITEMS_CFG;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
+// Per key type: 4-byte keys run 512 threads x 16 keys = 8192-key tiles, 2 blocks per SM in 64 registers.  A tile
+// leaves as 256 digit runs, so the tile size sets the run length (32 keys = 128 bytes at 8192) and divides the
+// per-tile look-back and barriers: 52.6 ms for the four passes against 55.9 at 4096 (4 blocks per SM) and 66.1 at
+// 16384 (one block per SM).  8-byte keys keep 256 threads x 16 keys, 3 blocks per SM in 80 registers.
+template <typename KeyT>
+struct RsCfg {
+    static constexpr int THREADS = sizeof(KeyT) == 4 ? RS_THREADS4_CFG : RS_THREADS;
+    static constexpr int MINB = sizeof(KeyT) == 4 ? 1024 / THREADS : 3;
+    static constexpr int TILE = THREADS * RS_ITEMS;
+    static constexpr int WARPS = THREADS / 32;
+};
 constexpr u32 RS_FLAG_AGG = 1u << 30;
 constexpr u32 RS_FLAG_INCL = 2u << 30;
 constexpr u32 RS_VAL_MASK = (1u << 30) - 1;
@@ -283,13 +294,13 @@ __global__ void __launch_bounds__(256) sort_scan_hist_kernel(const u32 *__restri
 
 template <typename KeyT>
 struct RsSmem {
-    u32 warp_hist[RS_WARPS][256];
+    u32 warp_hist[RsCfg<KeyT>::WARPS][256];
     u32 gofs[256];
     u32 warp_sums[8];
     u32 ticket;
     u32 pad[3];
-    KeyT keys[RS_TILE];
-    int vals[RS_TILE];
+    KeyT keys[RsCfg<KeyT>::TILE];
+    int vals[RsCfg<KeyT>::TILE];
 };
 
 template <typename KeyT>
@@ -311,23 +322,24 @@ __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return (u32)ld
     } while (0)
 
 template <typename KeyT, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 3) radix_pass_kernel(
+__global__ void __launch_bounds__(RsCfg<KeyT>::THREADS, RsCfg<KeyT>::MINB) radix_pass_kernel(
     const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in, KeyT *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
     int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {
+    constexpr int THREADS_ = RsCfg<KeyT>::THREADS, TILE_ = RsCfg<KeyT>::TILE, WARPS_ = RsCfg<KeyT>::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem<KeyT> &sm = *reinterpret_cast<RsSmem<KeyT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sm.ticket = atomicAdd(ticket_ctr, 1u);
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS_ * 256; i += THREADS_) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const u32 t = sm.ticket;
     // tile-major order: consecutive tickets are the same tile of different columns, so the
     // blocks in flight spread over all columns and every look-back chain stays short
     const int col = t % n_cols, tile = t / n_cols;
-    const int64_t base = (int64_t)tile * RS_TILE;
-    const int count = (int)min((int64_t)RS_TILE, N - base);
-    const bool full = count == RS_TILE;
+    const int64_t base = (int64_t)tile * TILE_;
+    const int count = (int)min((int64_t)TILE_, N - base);
+    const bool full = count == TILE_;
     const int shift = pass * 8;
     // everything below indexes with 32-bit tile-local offsets from these bases
     const KeyT *kin = keys_in + (int64_t)col * kstride + base;
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 
         // thread `tid` owns digit `tid`: exclusive offsets of the warps, tile total
         u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
+        for (int w = 0; w < WARPS_; ++w) {
             const u32 c = sm.warp_hist[w][tid];
             sm.warp_hist[w][tid] = run;
             run += c;
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 
         const u32 bstart = wofs + incl - total;
         // fold the digit's start into the warp offsets: a key's slot is warp_hist[w][d] + rank
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) sm.warp_hist[w][tid] += bstart;
+        for (int w = 0; w < WARPS_; ++w) sm.warp_hist[w][tid] += bstart;
         sm.gofs[tid] = gbase[((int64_t)col * 8 + pass) * 256 + tid] + excl - bstart;  // mod 2^32
     }
     __syncthreads();
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const u32 pos = my_hist[RS_DIGIT(i)] + rank[i];
-            DCHECK(pos < (u32)RS_TILE);
+            DCHECK(pos < (u32)TILE_);
             sm.keys[pos] = key[i];
             sm.vals[pos] = val[i];
         }
@@ -460,7 +472,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? RS_MINB_CFG : 
     int *vout = vals_out + (int64_t)col * vstride;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        const int pos = j * RS_THREADS + tid;
+        const int pos = j * THREADS_ + tid;
         if (full || pos < count) {
             const KeyT k = sm.keys[pos];
             const u32 dest = sm.gofs[(u32)(k >> shift) & 255u] + (u32)pos;
@@ -604,6 +616,7 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
     CK(cudaGetLastError());
     int *v[2] = {v0, v1};
     KeyT *k[2] = {keys0, keys1};
+    tiles = (int)((N + RsCfg<KeyT>::TILE - 1) / RsCfg<KeyT>::TILE);   // (status is sized for the smaller tile)
     u32 *ticket = status + (size_t)fb * tiles * 256;
     for (int p = 0; p < NPASS; ++p) {
         CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4 + 16, s));
@@ -617,13 +630,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
         const double bytes = (p == 0 ? 2 * K + 4 : last_plain ? K + 8 : 2 * K + 8) * (double)N * fb;
         LaunchScope ls(ctx, KC_SORT_PASS, bytes);
         if (p == 0)
-            radix_pass_kernel<KeyT, true, false><<<grid, RS_THREADS, pass_smem, s>>>(
+            radix_pass_kernel<KeyT, true, false><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
                 kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
         else if (last_plain)
-            radix_pass_kernel<KeyT, false, true><<<grid, RS_THREADS, pass_smem, s>>>(
+            radix_pass_kernel<KeyT, false, true><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
                 kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
         else
-            radix_pass_kernel<KeyT, false, false><<<grid, RS_THREADS, pass_smem, s>>>(
+            radix_pass_kernel<KeyT, false, false><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
                 kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
     }
     CK(cudaGetLastError());
