@@ -36,18 +36,22 @@ constexpr int RS_THREADS = 256;           // radix pass, 8-byte keys (4-byte key
 #define RS_ITEMS_CFG 16
 #endif
 #ifndef RS_THREADS4_CFG
-#define RS_THREADS4_CFG 512   // threads per block of the 4-byte-key pass
+#define RS_THREADS4_CFG 512   // threads per block of the 4-byte-key pass on wide column batches
+#endif
+#ifndef RS_BIG_TILE_MIN_COLS
+#define RS_BIG_TILE_MIN_COLS 128
 #endif
 constexpr int RS_ITEMS = RS_ITEMS_CFG;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
-constexpr int RS_WARPS = RS_THREADS / 32;
-// Per key type: 4-byte keys run 512 threads x 16 keys = 8192-key tiles, 2 blocks per SM in 64 registers.  A tile
-// leaves as 256 digit runs, so the tile size sets the run length (32 keys = 128 bytes at 8192) and divides the
-// per-tile look-back and barriers: 52.6 ms for the four passes against 55.9 at 4096 (4 blocks per SM) and 66.1 at
-// 16384 (one block per SM).  8-byte keys keep 256 threads x 16 keys, 3 blocks per SM in 80 registers.
-template <typename KeyT>
+// Block shape of the radix pass.  A tile leaves as 256 digit runs, so the tile size sets the run length and divides
+// the per-tile look-back and barriers: for 4-byte keys 512 threads x 16 keys (8192-key tiles, 2 blocks per SM in 64
+// registers) take 52.6 ms for the four passes of 256 columns against 55.9 at 4096 (4 blocks per SM) and 66.1 at
+// 16384 (one block per SM).  With few columns (a rank of a feature-sharded fit: 64 or 32) the smaller tile wins
+// (12.25 vs 12.77 ms at 64 columns, 6.19 vs 6.42 at 32: fewer, longer tiles in flight per look-back chain), so the
+// host picks the shape per column batch.  8-byte keys always run 256 threads, 3 blocks per SM in 80 registers.
+template <typename KeyT, int THREADS_P>
 struct RsCfg {
-    static constexpr int THREADS = sizeof(KeyT) == 4 ? RS_THREADS4_CFG : RS_THREADS;
+    static constexpr int THREADS = THREADS_P;
     static constexpr int MINB = sizeof(KeyT) == 4 ? 1024 / THREADS : 3;
     static constexpr int TILE = THREADS * RS_ITEMS;
     static constexpr int WARPS = THREADS / 32;
@@ -292,15 +296,15 @@ __global__ void __launch_bounds__(256) sort_scan_hist_kernel(const u32 *__restri
     gbase[(int64_t)blockIdx.x * 256 + tid] = base + incl - c;
 }
 
-template <typename KeyT>
+template <typename KeyT, int THREADS_P>
 struct RsSmem {
-    u32 warp_hist[RsCfg<KeyT>::WARPS][256];
+    u32 warp_hist[RsCfg<KeyT, THREADS_P>::WARPS][256];
     u32 gofs[256];
     u32 warp_sums[8];
     u32 ticket;
     u32 pad[3];
-    KeyT keys[RsCfg<KeyT>::TILE];
-    int vals[RsCfg<KeyT>::TILE];
+    KeyT keys[RsCfg<KeyT, THREADS_P>::TILE];
+    int vals[RsCfg<KeyT, THREADS_P>::TILE];
 };
 
 template <typename KeyT>
@@ -321,14 +325,15 @@ __device__ __forceinline__ u32 ld_stream_key<u32>(const u32 *p) { return (u32)ld
         }                                                                                                           \
     } while (0)
 
-template <typename KeyT, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(RsCfg<KeyT>::THREADS, RsCfg<KeyT>::MINB) radix_pass_kernel(
+template <typename KeyT, bool FIRST, bool LAST, int THREADS_P>
+__global__ void __launch_bounds__(RsCfg<KeyT, THREADS_P>::THREADS, RsCfg<KeyT, THREADS_P>::MINB) radix_pass_kernel(
     const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in, KeyT *__restrict__ keys_out,
     int *__restrict__ vals_out, const u32 *__restrict__ gbase, u32 *status, u32 *ticket_ctr, int64_t N,
     int64_t kstride, int64_t vstride, int tiles_per_col, int n_cols, int pass) {
-    constexpr int THREADS_ = RsCfg<KeyT>::THREADS, TILE_ = RsCfg<KeyT>::TILE, WARPS_ = RsCfg<KeyT>::WARPS;
+    using Cfg = RsCfg<KeyT, THREADS_P>;
+    constexpr int THREADS_ = Cfg::THREADS, TILE_ = Cfg::TILE, WARPS_ = Cfg::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem<KeyT> &sm = *reinterpret_cast<RsSmem<KeyT> *>(smem_raw);
+    RsSmem<KeyT, THREADS_P> &sm = *reinterpret_cast<RsSmem<KeyT, THREADS_P> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sm.ticket = atomicAdd(ticket_ctr, 1u);
     for (int i = tid; i < WARPS_ * 256; i += THREADS_) (&sm.warp_hist[0][0])[i] = 0;
@@ -580,6 +585,53 @@ __global__ void __launch_bounds__(256) sort_fixup_kernel(const double *__restric
     }
 }
 
+template <typename KeyT, int THREADS_P>
+int set_pass_attributes(b200dt_ctx *ctx) {
+    const int pass_smem = (int)sizeof(RsSmem<KeyT, THREADS_P>);
+    CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, false, THREADS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, pass_smem));
+    CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, false, THREADS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, pass_smem));
+    CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, true, THREADS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, pass_smem));
+    return 0;
+}
+
+// the passes alternate v0, v1, ...; the last one writes v1 (and, with keep_keys, the sorted keys into keys0).
+// `status` is sized for 4096-key tiles, the smallest shape.
+template <typename KeyT, int THREADS_P>
+int run_radix_passes(b200dt_ctx *ctx, int64_t N, int fb, KeyT *keys0, KeyT *keys1, int *v0, int *v1, int64_t col_stride,
+                     const u32 *gbase, u32 *status, bool keep_keys) {
+    using Cfg = RsCfg<KeyT, THREADS_P>;
+    constexpr int NPASS = (int)sizeof(KeyT);
+    cudaStream_t s = ctx->stream;
+    const size_t pass_smem = sizeof(RsSmem<KeyT, THREADS_P>);
+    int *v[2] = {v0, v1};
+    KeyT *k[2] = {keys0, keys1};
+    const int tiles = (int)((N + Cfg::TILE - 1) / Cfg::TILE);
+    u32 *ticket = status + (size_t)fb * tiles * 256;
+    for (int p = 0; p < NPASS; ++p) {
+        CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4 + 16, s));
+        const unsigned grid = (unsigned)((int64_t)fb * tiles);
+        const KeyT *kin = k[p & 1];
+        KeyT *kout = k[(p + 1) & 1];
+        const int *vin = v[(p + 1) & 1];
+        int *vout = v[p & 1];
+        const double K = (double)sizeof(KeyT);
+        const bool last_plain = p == NPASS - 1 && !keep_keys;
+        const double bytes = (p == 0 ? 2 * K + 4 : last_plain ? K + 8 : 2 * K + 8) * (double)N * fb;
+        LaunchScope ls(ctx, KC_SORT_PASS, bytes);
+        if (p == 0)
+            radix_pass_kernel<KeyT, true, false, THREADS_P><<<grid, Cfg::THREADS, pass_smem, s>>>(
+                kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+        else if (last_plain)
+            radix_pass_kernel<KeyT, false, true, THREADS_P><<<grid, Cfg::THREADS, pass_smem, s>>>(
+                kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+        else
+            radix_pass_kernel<KeyT, false, false, THREADS_P><<<grid, Cfg::THREADS, pass_smem, s>>>(
+                kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <typename KeyT>
 int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t ldx, KeyT *keys0, KeyT *keys1,
                    int *v0, int *v1, int64_t col_stride, u32 *ghist, u32 *gbase, u32 *status, int tiles,
@@ -590,14 +642,12 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
     cudaStream_t s = ctx->stream;
     const int groups = (fb + PREP_COLS - 1) / PREP_COLS;
     const size_t prep_smem = PREP_COLS * NPASS * 256 * 4 + PREP_COLS * PREP_PITCH * sizeof(KeyT);
-    const size_t pass_smem = sizeof(RsSmem<KeyT>);
     // (per context = per device: a process may drive several GPUs)
     const u32 attr_bit = sizeof(KeyT) == 4 ? 16u : 64u;   // this function is instantiated per key type
     if (!(ctx->attr_mask & attr_bit)) {
         CK(cudaFuncSetAttribute(sort_prepare_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-        CK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+        CKR((set_pass_attributes<KeyT, 256>(ctx)));
+        if constexpr (sizeof(KeyT) == 4) CKR((set_pass_attributes<KeyT, RS_THREADS4_CFG>(ctx)));
         ctx->attr_mask |= attr_bit;
     }
     CK(cudaMemsetAsync(ghist, 0, (size_t)groups * PREP_COLS * 8 * 256 * 4, s));
@@ -614,33 +664,13 @@ int run_radix_sort(b200dt_ctx *ctx, const double *dX, int64_t N, int fb, int64_t
         sort_scan_hist_kernel<<<fb * 8, 256, 0, s>>>(ghist, gbase);
     }
     CK(cudaGetLastError());
-    int *v[2] = {v0, v1};
-    KeyT *k[2] = {keys0, keys1};
-    tiles = (int)((N + RsCfg<KeyT>::TILE - 1) / RsCfg<KeyT>::TILE);   // (status is sized for the smaller tile)
-    u32 *ticket = status + (size_t)fb * tiles * 256;
-    for (int p = 0; p < NPASS; ++p) {
-        CK(cudaMemsetAsync(status, 0, (size_t)fb * tiles * 256 * 4 + 16, s));
-        const unsigned grid = (unsigned)((int64_t)fb * tiles);
-        const KeyT *kin = k[p & 1];
-        KeyT *kout = k[(p + 1) & 1];
-        const int *vin = v[(p + 1) & 1];
-        int *vout = v[p & 1];
-        const double K = (double)sizeof(KeyT);
-        const bool last_plain = p == NPASS - 1 && !keep_keys;
-        const double bytes = (p == 0 ? 2 * K + 4 : last_plain ? K + 8 : 2 * K + 8) * (double)N * fb;
-        LaunchScope ls(ctx, KC_SORT_PASS, bytes);
-        if (p == 0)
-            radix_pass_kernel<KeyT, true, false><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
-                kin, nullptr, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-        else if (last_plain)
-            radix_pass_kernel<KeyT, false, true><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
-                kin, vin, nullptr, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
-        else
-            radix_pass_kernel<KeyT, false, false><<<grid, RsCfg<KeyT>::THREADS, pass_smem, s>>>(
-                kin, vin, kout, vout, gbase, status, ticket, N, N, col_stride, tiles, fb, p);
+    // 4-byte keys: big tiles when the batch has enough columns to keep every look-back chain short
+    if constexpr (sizeof(KeyT) == 4) {
+        if (fb >= RS_BIG_TILE_MIN_COLS)
+            return run_radix_passes<KeyT, RS_THREADS4_CFG>(ctx, N, fb, keys0, keys1, v0, v1, col_stride, gbase, status,
+                                                           keep_keys);
     }
-    CK(cudaGetLastError());
-    return 0;
+    return run_radix_passes<KeyT, 256>(ctx, N, fb, keys0, keys1, v0, v1, col_stride, gbase, status, keep_keys);
 }
 
 }  // namespace
