@@ -77,17 +77,12 @@ def fit_sharded(X_local, y, col_offset, n_features, last_col=None, criterion=_li
     X_local = X_local.contiguous()
     y = y.contiguous()
     N, F_local = X_local.shape
-    lc_ptr, lc_ld = None, 0
-    if last_col is not None and col_offset + F_local != n_features:
-        if last_col.is_cuda != on_device:
-            raise TypeError("last_col must live where X_local lives")
-        lc_ptr, lc_ld = last_col.data_ptr(), last_col.stride(0)
     space = _lib.DEVICE if on_device else _lib.HOST
     lib, h = ctx.lib, ctx.handle
     ctx.check(lib.b200dt_session_begin(h, X_local.data_ptr(), y.data_ptr(), N, F_local, X_local.stride(0),
                                        space, criterion, int(max_depth), float(min_improvement),
                                        int(min_sample_leaf), 1 if v == 1 else 2, int(col_offset),
-                                       int(n_features), lc_ptr, lc_ld))
+                                       int(n_features), None, 0))
     mask = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
     n_live = ctypes.c_int64()
     need_part, need_exact = ctypes.c_int(), ctypes.c_int()
