@@ -7,9 +7,9 @@
 //
 //  * 64-bit path (always correct): 8 onesweep passes of 8-bit digits over the full key.
 //      prepare 16 B + passes 20 + 6*24 + 16 = 196 algorithmic bytes per element.
-//  * 32-bit path (default, falls back per column): the radix passes are bound by their scattered
-//    DRAM traffic (ncu: 56 % of peak bytes/s; cutting instructions changed nothing), so the lever
-//    is fewer bytes.  Sort a 32-bit order-preserving IMAGE of the key (linear quantisation of the
+//  * 32-bit path (default, falls back per column): a radix pass costs the same per key whatever
+//    the key width (a latency chain per tile; cutting instructions changed nothing), so the lever
+//    is fewer bytes and passes.  Sort a 32-bit order-preserving IMAGE of the key (linear quantisation of the
 //    value between the column's min and max; 4 passes of 4-byte keys), then one fix-up pass streams
 //    the sorted images, gathers the full key only of elements whose image is shared (~1 % for smooth
 //    data) and stably sorts those short runs.  min/max 8 + prepare 12 + passes 12+16+16+16 + fix-up
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(RsCfg<KeyT, THREADS_P>::THREADS, RsCfg<KeyT, T
             key[i] = o0 + i * 32 < count ? ld_stream_key<KeyT>(kin + o0 + i * 32) : (KeyT)~(KeyT)0;
     }
     // stable rank of each key among the keys of its warp with the same digit.  All peer masks
-    // first (independent match.any's pipeline), then, item by item, one shared atomic per distinct
+    // first (independent ballots pipeline), then, item by item, one shared atomic per distinct
     // digit by its lowest lane, whose old count is broadcast to the peers; items are issued in
     // order, so the per-digit counts accumulate in the stable order.
     const u32 lt = lanemask_lt();
