@@ -168,3 +168,18 @@ def test_classification_mirror_host_side_checks():
     a = strategy.surrogate_gini_improvements(cum, np.arange(1, 21)[:, np.newaxis])
     b = strategy.surrogate_gini_improvements(cum[:-1], np.arange(1, 20)[:, np.newaxis], cum[-1], 20)
     assert a.shape == (19, 1) and np.array_equal(a, b)
+
+
+def test_variant_library_override(monkeypatch):
+    """B200DT_LIB (tuning builds, scripts/build_variant.sh) replaces the default library and fails loudly when the
+    file is missing -- never a silent fall back to the default build."""
+    from np_decision_tree_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("B200DT_LIB", "/nonexistent/libb200tree_variant.so")
+    with pytest.raises(_lib.B200Error):
+        _lib.load()
+    monkeypatch.setenv("B200DT_LIB", _lib.LIB_PATH)
+    monkeypatch.setattr(_lib, "_lib", None)
+    lib = _lib.load()
+    assert hasattr(lib, "b200dt_session_begin") and lib.b200dt_abi_version() > 0
+    monkeypatch.setattr(_lib, "_lib", None)   # the next user loads the default again
