@@ -38,6 +38,9 @@ constexpr int RS_THREADS = 256;           // radix pass, 8-byte keys (4-byte key
 #ifndef RS_THREADS4_CFG
 #define RS_THREADS4_CFG 512   // threads per block of the 4-byte-key pass on wide column batches
 #endif
+#ifndef RS_BATCH_COLS
+#define RS_BATCH_COLS 32      // columns per sort batch (B200DT_SORT_BATCH overrides): see sort_columns_device
+#endif
 #ifndef RS_BIG_TILE_MIN_COLS
 #define RS_BIG_TILE_MIN_COLS 128
 #endif
@@ -701,6 +704,15 @@ int sort_columns_device(b200dt_ctx *ctx, const double *dX, int64_t N, int64_t F,
         const size_t cap = (size_t)24 << 30;
         if (budget > cap) budget = cap;
         fb_max = (int64_t)(budget / (16ull * (size_t)N));
+    }
+    {
+        // columns per sort batch: a pass over fewer columns keeps fewer scatter streams open (256 per column) and
+        // is faster per column -- four passes over 256 columns take 52.5 ms in batches of 128 (8192-key tiles),
+        // 52.7 in batches of 64, 49.0 in batches of 32, 48.9 / 49.6 in batches of 24 / 16 (where prepare loses more
+        // than the passes gain).  Ranks of a feature-sharded fit and host-resident inputs already came in 32s.
+        int64_t cap = RS_BATCH_COLS;
+        if (const char *e = getenv("B200DT_SORT_BATCH")) cap = std::max<int64_t>(PREP_COLS, atoll(e));
+        if (fb_max > cap) fb_max = cap;
     }
     fb_max = (fb_max / PREP_COLS) * PREP_COLS;
     if (fb_max < PREP_COLS) fb_max = PREP_COLS;

@@ -318,6 +318,16 @@ def test_bulk_copy_scan_builds_the_same_tree(monkeypatch, seed, n, F, depth, yr,
     assert_same_tree(one.build_regression_tree(X, y, max_depth=depth, v=v), want, what=f"bulk scan seed {seed}")
 
 
+def test_wide_sort_batches_use_the_big_radix_tile(monkeypatch):
+    """B200DT_SORT_BATCH >= 128 sorts 128+ columns per batch with the 512-thread / 8192-key radix shape (the default
+    batch of 32 columns uses 4096-key tiles): partial last tile, more than one tile per column, same tree."""
+    from np_decision_tree_b200.decision_tree import one
+    monkeypatch.setenv("B200DT_SORT_BATCH", "256")
+    X, y = small_problem(77, 20011, 132, None)
+    want = oracle.fit_l2(X, y, max_depth=3, v=1, sort_kind="stable")
+    assert_same_tree(one.build_regression_tree(X, y, max_depth=3, v=1), want, what="wide sort batch")
+
+
 def test_pageable_strided_host_input_takes_the_bounce_pipeline(dt):
     """>= 64 MB of ordinary (pageable) host memory with a row stride larger than F: packed into pinned slots by host
     threads, column batch by column batch (csrc/fit.cu: bounce_start) -- same tree as the contiguous / device paths."""
